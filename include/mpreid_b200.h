@@ -1,0 +1,156 @@
+/*
+ * mpreid_b200 — C ABI of the B200-native MP-ReID evaluation / retrieval hot path.
+ *
+ * The reference (MP-ReID/mp-reid) is pure Python: its "FFI" for this path is the set of functions
+ * in utils/metrics.py and utils/reranking.py.  Each entry point below names the reference lines it
+ * replaces.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 on success or a negative MPREID_ERR_* code,
+ *     the message is available from mpreid_last_error() (thread-local);
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all buffers;
+ *   - every call takes the CUDA stream to launch on (cudaStream_t passed as void*), never
+ *     synchronises it and never allocates; workspaces are sized by the *_workspace_bytes queries;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - labels (pid / camid) are int64, as numpy gives them; INT64_MIN is reserved.
+ */
+#ifndef MPREID_B200_H
+#define MPREID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPREID_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MPREID_API __attribute__((visibility("default")))
+#else
+#define MPREID_API
+#endif
+
+enum mpreid_error {
+  MPREID_OK = 0,
+  MPREID_ERR_INVALID = -1,    /* bad argument                                   */
+  MPREID_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed            */
+  MPREID_ERR_UNSUPPORTED = -3,/* e.g. tcgen05 path requested on a non-sm_100 GPU */
+  MPREID_ERR_WORKSPACE = -4   /* workspace too small                            */
+};
+
+/* distance epilogues */
+enum mpreid_metric {
+  MPREID_SQEUCLID = 0,      /* ||q||^2+||g||^2-2q.g, no sqrt, no clamp   utils/metrics.py:7-13          */
+  MPREID_ARCCOS = 1,        /* arccos(clip(q.g/(|q||g|), +-(1-1e-5)))    utils/metrics.py:15-25         */
+  MPREID_ONE_MINUS_DOT = 2, /* 1 - q.g                      processor/processor_uniprompt_stage2.py:466 */
+  MPREID_SQRT_EUCLID = 3    /* sqrt(clamp(sqeuclid, 1e-12))              loss/triplet_loss.py:16-31     */
+};
+
+/* how the q.g contraction is computed */
+enum mpreid_precision {
+  MPREID_FP32_SIMT = 0, /* plain fp32 FFMA tiles (validation / tiny shapes)                        */
+  MPREID_3XTF32 = 1,    /* tcgen05 kind::tf32, error-compensated hi/lo split: fp32-accurate        */
+  MPREID_BF16 = 2       /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate             */
+};
+
+enum mpreid_junk {
+  MPREID_JUNK_NONE = 0,   /* HEAD behaviour: utils/metrics.py:55 (remove = False)                  */
+  MPREID_JUNK_PID_CAM = 1 /* same pid AND same camid removed: utils/metrics.py:54 (commented),
+                             processor/processor_uniprompt_stage2.py:483-488 (live)                */
+};
+
+MPREID_API const char* mpreid_last_error(void);
+MPREID_API int mpreid_abi_version(void);
+/* sm count, compute capability and whether the tcgen05 kernels can run on `device` */
+MPREID_API int mpreid_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
+
+/* ---- feature preparation -------------------------------------------------------------------
+ * Replaces torch.nn.functional.normalize(feats, dim=1, p=2) (utils/metrics.py:114) and the
+ * torch.pow(x,2).sum(1) terms of utils/metrics.py:10-11 / utils/reranking.py:38-39 in ONE pass
+ * over x, and emits the tensor-core operand planes:
+ *   xn      [rows, D]   fp32, normalised (or copied) features             (may be NULL)
+ *   sqnorm  [rows]      fp32, sum of squares of the xn row                (may be NULL)
+ *   norm    [rows]      fp32, sqrt of the above                           (may be NULL)
+ *   hi, lo  [rows, Dp]  fp32 holding TF32-representable values, xn = hi + lo (+2^-22 rel.), zero
+ *                       padded from D to Dp                                (both or neither)
+ *   bf      [rows, Dp]  bf16 (round-to-nearest-even) copy of xn, zero padded (may be NULL)
+ * Dp must be a multiple of 32 (TMA boxes are 128 B wide).  x may be fp32 only.            */
+MPREID_API int mpreid_prep_rows(const float* x, int64_t rows, int64_t D, int64_t ld_x, int normalize,
+                     float* xn, int64_t ld_xn, float* sqnorm, float* norm,
+                     float* hi, float* lo, uint16_t* bf, int64_t Dp, void* stream);
+
+/* ---- distance matrix --------------------------------------------------------------------------
+ * Replaces euclidean_distance (utils/metrics.py:7-13), cosine_similarity (utils/metrics.py:15-25),
+ * the inline 1-q.g (processor_uniprompt_stage2.py:466-468) and the all-pairs matrix of
+ * utils/reranking.py:36-41.
+ *   precision MPREID_FP32_SIMT : qa/ga = fp32 features [*, ldk]; qb/gb ignored
+ *   precision MPREID_3XTF32    : qa/ga = hi planes, qb/gb = lo planes, [*, ldk] fp32, ldk % 32 == 0
+ *   precision MPREID_BF16      : qa/ga = bf16 planes [*, ldk], ldk % 64 == 0;    qb/gb ignored
+ *   q_aux/g_aux: squared norms for the euclidean metrics, norms for MPREID_ARCCOS, unused (may be
+ *   NULL) for MPREID_ONE_MINUS_DOT.
+ *   row_max (optional, [Q], must be pre-filled with -inf): per-row maximum of the written values
+ *   (the column max of utils/reranking.py:46, by symmetry).                                    */
+MPREID_API int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga, const void* gb,
+                       const float* q_aux, const float* g_aux,
+                       int64_t Q, int64_t G, int64_t K, int64_t ldk,
+                       int metric, int precision,
+                       float* out, int64_t ld_out, float* row_max, void* stream);
+
+/* ---- ranking + CMC / AP ------------------------------------------------------------------------
+ * Replaces eval_func (utils/metrics.py:28-88).  The Q x G argsort is never formed: for every query
+ * the kernel takes the gallery entries with the query's pid (a hash-grouped label index), sorts
+ * those few (distance, index) keys and counts, in ONE streaming pass over the distance row, how
+ * many entries precede each of them under the stable order (distance, then gallery index) ==
+ * np.argsort(kind='stable').  Outputs per query:
+ *   first_hit [Q] int32  1-based rank (after junk removal) of the first correct match, 0 = the
+ *                        query's pid is absent from the (kept) gallery            (:61-63)
+ *   ap        [Q] fp64   average precision, bit-equal to the float64 numpy expression of :73-79
+ *                        (numpy's pairwise summation order is emulated)
+ *   num_rel   [Q] int32  number of correct matches                                 (:73)
+ * The final cmc = float32 sum / num_valid and mAP = np.mean (:84-86) are left to the host so that
+ * they are computed by numpy itself on the gathered per-query values (also across GPUs).
+ * status_host semantics: the call is asynchronous; `status` (device, int32[4]) receives
+ *   [0] overflow flag (workspace `pos_capacity` too small), [1] entries needed, [2] max positives
+ *   of any query, [3] reserved.                                                                  */
+MPREID_API size_t mpreid_rank_eval_workspace_bytes(int64_t Q, int64_t G, int64_t pos_capacity);
+MPREID_API int mpreid_rank_eval(const float* dist, int64_t ld_dist, int64_t Q, int64_t G,
+                     const int64_t* q_pid, const int64_t* g_pid,
+                     const int64_t* q_cam, const int64_t* g_cam, int junk_mode,
+                     int32_t* first_hit, double* ap, int32_t* num_rel,
+                     void* workspace, size_t workspace_bytes, int64_t pos_capacity,
+                     int32_t* status, void* stream);
+
+/* ---- per-row top-k ---------------------------------------------------------------------------
+ * The first k entries of np.argsort(row / row_scale, kind='stable') (utils/reranking.py:46-48 with
+ * k = k1+1; retrieval top-100).  row_scale may be NULL (no division).  idx [Q,k] int32, val [Q,k]
+ * fp32 (the divided values; may be NULL).  Entries beyond min(k,G) are -1 / +inf.              */
+MPREID_API int mpreid_row_topk(const float* dist, int64_t ld_dist, int64_t Q, int64_t G, int k,
+                    const float* row_scale, int32_t* idx, float* val, void* stream);
+MPREID_API int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int64_t G, float* row_max, void* stream);
+
+/* ---- k-reciprocal re-ranking (utils/reranking.py:29-100) --------------------------------------
+ * `dist` is the all-pairs matrix in the orientation dist[i][j] = reference distmat[j][i] (:46
+ * transposes), N = Q + G rows.  One call runs: row max + top-(k1+1) (:46-48), k-reciprocal sets
+ * with the 2/3 expansion rule and the Gaussian-kernel V rows in fp16 (:51-71), k2 query expansion
+ * (:73-78), inverted index (:80-82), Jaccard distance with the fp16 accumulator (:84-93) and the
+ * lambda blend (:95), writing final[Q, G] fp32 (:99).  fp16 rounding points are the reference's. */
+MPREID_API size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, int k2);
+MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, int64_t N, int64_t Q, int k1, int k2, float lambda_value,
+                  float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
+                  int32_t* status, void* stream);
+
+/* ---- host-side hooks (no GPU needed) -----------------------------------------------------------
+ * The scalar arithmetic the kernels run is __host__ __device__ code; these two entry points run it
+ * on the CPU so the CPU-only test-suite can check it bit-for-bit against numpy.
+ *   mpreid_host_average_precision: AP of one query from the ascending 1-based ranks of its m
+ *     correct matches in a kept list of n entries (utils/metrics.py:73-79, numpy pairwise order).
+ *   mpreid_host_order_keys: the 32-bit sort key of each fp32 value (numpy sort order).             */
+MPREID_API double mpreid_host_average_precision(const int32_t* ranks_host, int m, int64_t n);
+MPREID_API void mpreid_host_order_keys(const float* values_host, int64_t n, uint32_t* keys_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPREID_B200_H */

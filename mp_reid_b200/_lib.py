@@ -1,0 +1,82 @@
+"""ctypes binding of libmpreid_b200.so (C ABI: include/mpreid_b200.h).
+
+The library is the product; there is no Python / CPU fallback.  If the shared object is missing it
+is built in-tree with nvcc (mp_reid_b200/build.py); if that is impossible the import of the compute
+path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpreid_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "mpreid_b200.h")
+
+# enums of include/mpreid_b200.h
+SQEUCLID, ARCCOS, ONE_MINUS_DOT, SQRT_EUCLID = 0, 1, 2, 3
+FP32_SIMT, X3TF32, BF16 = 0, 1, 2
+JUNK_NONE, JUNK_PID_CAM = 0, 1
+
+METRICS = {"sqeuclid": SQEUCLID, "euclidean": SQEUCLID, "arccos": ARCCOS, "cosine": ARCCOS,
+           "one_minus_dot": ONE_MINUS_DOT, "1-cos": ONE_MINUS_DOT, "sqrt_euclid": SQRT_EUCLID}
+PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "fp32": X3TF32, "3xtf32": X3TF32, "bf16": BF16}
+JUNKS = {"none": JUNK_NONE, "pid_cam": JUNK_PID_CAM}
+
+_p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+
+SIGNATURES = {
+    "mpreid_last_error": (C.c_char_p, []),
+    "mpreid_abi_version": (_i32, []),
+    "mpreid_device_info": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "mpreid_prep_rows": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "mpreid_dist_matrix": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
+    "mpreid_rank_eval_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "mpreid_rank_eval": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _sz, _i64, _p, _p]),
+    "mpreid_row_topk": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "mpreid_row_max": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
+    "mpreid_rerank_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "mpreid_rerank": (_i32, [_p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p, _p]),
+    "mpreid_host_average_precision": (C.c_double, [_p, _i32, _i64]),
+    "mpreid_host_order_keys": (None, [_p, _i64, _p]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every entry point include/mpreid_b200.h declares (used by the ABI test)."""
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"MPREID_API[^;(]*?\b(mpreid_\w+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python -m mp_reid_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mpreid_abi_version() != 1:
+        raise RuntimeError("libmpreid_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class MpreidError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().mpreid_last_error().decode(errors="replace")
+        raise MpreidError(f"{what or 'mpreid call'} failed (code {rc}): {msg}")

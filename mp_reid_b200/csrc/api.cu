@@ -1,0 +1,79 @@
+// C-ABI plumbing: error reporting, device queries, the distance-matrix dispatcher.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mpreid {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count_of_current_device() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int launch_dist_simt(const float* q, const float* g, const float* q_aux, const float* g_aux, int64_t Q, int64_t G,
+                     int64_t K, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st);
+int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
+                   int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
+                   float* row_max, cudaStream_t st);
+
+}  // namespace mpreid
+
+using namespace mpreid;
+
+extern "C" const char* mpreid_last_error(void) { return g_err; }
+extern "C" int mpreid_abi_version(void) { return MPREID_ABI_VERSION; }
+
+extern "C" int mpreid_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05) {
+  cudaDeviceProp p;
+  MPREID_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (has_tcgen05) *has_tcgen05 = (p.major == 10) ? 1 : 0;
+  return MPREID_OK;
+}
+
+extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga, const void* gb,
+                                  const float* q_aux, const float* g_aux,
+                                  int64_t Q, int64_t G, int64_t K, int64_t ldk,
+                                  int metric, int precision,
+                                  float* out, int64_t ld_out, float* row_max, void* stream) {
+  MPREID_REQUIRE(qa && ga && out, "dist_matrix: null operand");
+  MPREID_REQUIRE(Q > 0 && G > 0 && K > 0 && ldk >= K && ld_out >= G && Q < INT32_MAX && G < INT32_MAX,
+                 "dist_matrix: bad shape Q=%lld G=%lld K=%lld ldk=%lld ld_out=%lld", (long long)Q, (long long)G,
+                 (long long)K, (long long)ldk, (long long)ld_out);
+  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_SQRT_EUCLID, "dist_matrix: unknown metric %d", metric);
+  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || (q_aux && g_aux), "dist_matrix: metric %d needs q_aux/g_aux", metric);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MPREID_FP32_SIMT)
+    return launch_dist_simt((const float*)qa, (const float*)ga, q_aux, g_aux, Q, G, K, ldk, metric, out, ld_out, row_max, st);
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16, "dist_matrix: unknown precision %d", precision);
+  MPREID_REQUIRE(precision != MPREID_3XTF32 || (qb && gb), "dist_matrix: 3xTF32 needs the lo planes");
+  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, precision, out, ld_out, row_max, st);
+}
+
+extern "C" double mpreid_host_average_precision(const int32_t* ranks_host, int m, int64_t n) {
+  if (!ranks_host || m <= 0) return 0.0;
+  return pairwise_sparse_sum(ranks_host, m, n) / (double)m;
+}
+
+extern "C" void mpreid_host_order_keys(const float* values_host, int64_t n, uint32_t* keys_host) {
+  for (int64_t i = 0; i < n; ++i) keys_host[i] = order_key(values_host[i]);
+}

@@ -1,0 +1,162 @@
+// Shared helpers for the mpreid_b200 kernels (host+device scalar code lives here so that the
+// CPU unit tests can exercise exactly the arithmetic the kernels run).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/mpreid_b200.h"
+
+#define HD __host__ __device__ __forceinline__
+
+namespace mpreid {
+
+void set_error(const char* fmt, ...);
+
+#define MPREID_CUDA_CHECK(expr)                                                              \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::mpreid::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MPREID_ERR_CUDA;                                                                \
+    }                                                                                        \
+  } while (0)
+
+#define MPREID_REQUIRE(cond, ...)                                                            \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ::mpreid::set_error(__VA_ARGS__);                                                      \
+      return MPREID_ERR_INVALID;                                                             \
+    }                                                                                        \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count_of_current_device();
+
+// ---------------------------------------------------------------------------------------------
+// Total order on fp32 that reproduces numpy's sort order: ascending value, -0.0 == +0.0, every NaN
+// last (all NaNs tie).  Ties are then broken by the gallery index (== kind='stable').
+// ---------------------------------------------------------------------------------------------
+HD uint32_t f32_bits(float v) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(v);
+#else
+  union { float f; uint32_t u; } c; c.f = v; return c.u;
+#endif
+}
+HD float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+HD uint32_t order_key(float v) {
+  uint32_t u = f32_bits(v + 0.0f);                // -0.0 -> +0.0
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;  // NaN
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+HD float order_key_inv(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return bits_f32(u);
+}
+HD uint64_t make_key(float v, uint32_t idx) { return ((uint64_t)order_key(v) << 32) | idx; }
+
+// ---------------------------------------------------------------------------------------------
+// Average precision exactly as numpy evaluates utils/metrics.py:73-79:
+//   tmp = cumsum(match) / arange(1..n) * match ; AP = tmp.sum() / num_rel      (float64)
+// tmp is zero except at the positions of the correct matches, so the sum is a function of the
+// sorted 0-based positions pos[0..m) only -- but numpy adds with its pairwise scheme
+// (blocks <= 128 with 8 strided accumulators, recursive halving rounded to a multiple of 8), and
+// float64 addition is not associative, so the same tree is walked here over the sparse terms.
+// term(i) = double(i+1) / double(pos[i]+1).
+// ---------------------------------------------------------------------------------------------
+// `rank` holds the 1-based ranks of the correct matches, ascending; position = rank - 1.
+HD double ap_term(const int32_t* rank, int i) { return (double)(i + 1) / (double)rank[i]; }
+
+HD int lower_bound_pos(const int32_t* rank, int a, int b, int64_t x) {  // first i in [a,b) with rank[i]-1 >= x
+  while (a < b) {
+    int mid = (a + b) >> 1;
+    if ((int64_t)rank[mid] - 1 < x) a = mid + 1; else b = mid;
+  }
+  return a;
+}
+
+HD double pairwise_leaf(const int32_t* rank, int64_t lo, int64_t n, int a, int b) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = a; i < b; ++i) res = res + ap_term(rank, i);
+    return res;
+  }
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
+  const int64_t body_end = lo + (n - (n % 8));
+  int i = a;
+  for (; i < b && (int64_t)rank[i] - 1 < body_end; ++i) {
+    const double t = ap_term(rank, i);
+    switch (((int64_t)rank[i] - 1 - lo) & 7) {
+      case 0: r0 += t; break; case 1: r1 += t; break; case 2: r2 += t; break; case 3: r3 += t; break;
+      case 4: r4 += t; break; case 5: r5 += t; break; case 6: r6 += t; break; default: r7 += t; break;
+    }
+  }
+  double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  for (; i < b; ++i) res = res + ap_term(rank, i);
+  return res;
+}
+
+// sum of the length-n vector whose non-zeros sit at positions rank[0..m)-1 (ascending), numpy pairwise order
+HD double pairwise_sparse_sum(const int32_t* rank, int m, int64_t n) {
+  struct Frame { int64_t lo, n; int a, b, mid, stage; double left; };
+  Frame st[48];
+  int sp = 1;
+  st[0].lo = 0; st[0].n = n; st[0].a = 0; st[0].b = m; st[0].stage = 0; st[0].mid = 0; st[0].left = 0.0;
+  double ret = 0.0;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.stage == 0) {
+      if (f.a == f.b) { ret = 0.0; --sp; continue; }
+      if (f.n <= 128) { ret = pairwise_leaf(rank, f.lo, f.n, f.a, f.b); --sp; continue; }
+      int64_t n2 = f.n / 2; n2 -= n2 % 8;
+      f.mid = lower_bound_pos(rank, f.a, f.b, f.lo + n2);
+      f.stage = 1;
+      Frame& c = st[sp++];
+      c.lo = f.lo; c.n = n2; c.a = f.a; c.b = f.mid; c.stage = 0;
+    } else if (f.stage == 1) {
+      f.left = ret;
+      f.stage = 2;
+      int64_t n2 = f.n / 2; n2 -= n2 % 8;
+      Frame& c = st[sp++];
+      c.lo = f.lo + n2; c.n = f.n - n2; c.a = f.mid; c.b = f.b; c.stage = 0;
+    } else {
+      ret = f.left + ret;
+      --sp;
+    }
+  }
+  return ret;
+}
+
+// np.around(k1 / 2) -- round half to even (utils/reranking.py:60)
+HD int round_half_even_div2(int k1) {
+  int h = k1 / 2;
+  if (k1 & 1) return (h & 1) ? h + 1 : h;  // x.5 -> nearest even
+  return h;
+}
+
+HD uint32_t next_pow2_u32(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+HD uint64_t mix64(uint64_t x) {  // splitmix64 finaliser, hashes pids into the label table
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+}  // namespace mpreid

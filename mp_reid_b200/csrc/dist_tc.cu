@@ -1,0 +1,388 @@
+// Distance matrix on the 5th-generation tensor cores (sm_100a): TMA -> shared memory -> tcgen05.mma
+// -> TMEM -> fused distance epilogue.  Replaces the torch-CPU sgemm of utils/metrics.py:12,17 and
+// utils/reranking.py:40.
+//
+//   out[i, j] = epilogue( sum_k q[i,k] * g[j,k] )         both operands K-major ("NT" GEMM)
+//
+// Precision modes
+//   3xTF32  the fp32 operands are pre-split (prep.cu) into TF32-exact planes  x = hi + lo;  the
+//           accumulator receives  lo*hi + hi*lo + hi*hi  (error ~2^-21 relative per product, i.e.
+//           fp32-level; the lo*lo term is below fp32 rounding).  Three kind::tf32 MMAs per k-step.
+//   BF16    bf16-rounded operands, one kind::f16 MMA per k-step, fp32 accumulate.
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads = 6 warps
+//   warp 0      TMA producer (one elected lane): 128B-swizzled boxes of 128 B x {128|256} rows
+//   warp 1      TMEM allocator + MMA issuer (one elected lane), 128x256 fp32 accumulator in TMEM,
+//               double buffered (2 x 256 of the 512 columns) so the epilogue of tile i overlaps the
+//               MMAs of tile i+1
+//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, norm add / arccos / 1-dot, row max,
+//               store.  Warp w owns TMEM lanes 32*(w%4)..+31 (hardware restriction), i.e. one output
+//               row per thread.
+// Tiles are visited band-major (16 m-blocks per band, m fastest) so the query band stays in L2 and
+// every gallery tile is fetched from HBM once per band.
+#include <cuda.h>
+
+#include "epilogue.cuh"
+
+namespace mpreid {
+namespace tc {
+
+static constexpr int BM = 128;       // UMMA_M
+static constexpr int BN = 256;       // UMMA_N
+static constexpr int ROW_BYTES = 128;  // K bytes per smem row = one 128B swizzle atom
+static constexpr int THREADS = 192;
+static constexpr int TMEM_COLS = 512;
+static constexpr int BAND = 16;      // m-blocks per L2 band
+
+template <int PREC> struct Cfg;
+template <> struct Cfg<MPREID_3XTF32> {
+  static constexpr int PLANES = 2, ELEM = 4, UMMA_K = 8, STAGES = 2, FMT = 2 /*TF32*/;
+};
+template <> struct Cfg<MPREID_BF16> {
+  static constexpr int PLANES = 1, ELEM = 2, UMMA_K = 16, STAGES = 4, FMT = 1 /*BF16*/;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int PREC>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (PREC == MPREID_3XTF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+// bits: [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor: c_format F32 (bit 4), a/b format (bits 7-9 / 10-12), K-major both,
+// N>>3 at bits 17-22, M>>4 at bits 24-28
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TileCoord { int m_blk, n_blk; };
+__device__ __forceinline__ TileCoord decode_tile(int tile, int m_blocks, int n_blocks) {
+  const int band_tiles = BAND * n_blocks;
+  const int b = tile / band_tiles;
+  const int rem = tile - b * band_tiles;
+  const int h = min(BAND, m_blocks - b * BAND);
+  TileCoord t;
+  t.n_blk = rem / h;
+  t.m_blk = b * BAND + (rem - t.n_blk * h);
+  return t;
+}
+
+struct Maps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+template <int PREC, bool VEC>
+__global__ void __launch_bounds__(THREADS, 1)
+k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
+          int Q, int G, int num_k_blocks, int metric, float* __restrict__ out, int64_t ld_out,
+          float* __restrict__ row_max, int m_blocks, int n_blocks) {
+  using C = Cfg<PREC>;
+  constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
+  constexpr int STAGE_BYTES = C::PLANES * (A_PLANE + B_PLANE);
+  constexpr int K_PER_BLOCK = ROW_BYTES / C::ELEM;       // elements of K per stage
+  constexpr int K_STEPS = K_PER_BLOCK / C::UMMA_K;       // 4
+  constexpr uint32_t IDESC = make_idesc(C::FMT, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-B aligned tiles
+  const uint32_t bar_base = base + C::STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.b_hi);
+    if (C::PLANES == 2) { prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_lo); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const int kc = kb * K_PER_BLOCK;
+          tma_load_2d(sa, &maps.a_hi, full_bar(stage), kc, t.m_blk * BM);
+          if (C::PLANES == 2) tma_load_2d(sa + A_PLANE, &maps.a_lo, full_bar(stage), kc, t.m_blk * BM);
+          const uint32_t sb = sa + C::PLANES * A_PLANE;
+          tma_load_2d(sb, &maps.b_hi, full_bar(stage), kc, t.n_blk * BN);
+          if (C::PLANES == 2) tma_load_2d(sb + B_PLANE, &maps.b_lo, full_bar(stage), kc, t.n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(as), aph ^ 1u);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + C::PLANES * A_PLANE;
+          const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < K_STEPS; ++k) {
+            const uint64_t koff = (uint64_t)((k * C::UMMA_K * C::ELEM) >> 4);  // +32 B per k-step inside the atom
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (C::PLANES == 2) {
+              const uint64_t a_lo = make_smem_desc(sa + A_PLANE), b_lo = make_smem_desc(sb + B_PLANE);
+              umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
+              umma<PREC>(tmem_d, a_hi + koff, b_lo + koff, IDESC, 1u);
+              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
+            } else {
+              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, acc);
+            }
+          }
+          umma_commit(empty_bar(stage));                       // smem slot reusable once these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(tfull_bar(as));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
+      const int as = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int gm = t.m_blk * BM + row;
+      const bool row_ok = gm < Q;
+      const float qa = (row_ok && q_aux) ? q_aux[gm] : 0.f;
+      float* orow = out + (int64_t)gm * ld_out;
+      float rmax = -INFINITY;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int gn0 = t.n_blk * BN + c0;
+        if (row_ok && gn0 < G) {
+          float d[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = gn0 + j;
+            const float ga = (g_aux && gn < G) ? __ldg(g_aux + gn) : 1.f;
+            d[j] = finish_distance_rt(metric, __uint_as_float(r[j]), qa, ga);
+            if (gn < G) rmax = fmaxf(rmax, d[j]);
+          }
+          if (VEC && gn0 + 32 <= G) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + gn0 + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < G) orow[gn0 + j] = d[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (row_max && row_ok && rmax > -INFINITY) atomic_max_f32(&row_max[gm], rmax);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, int elem, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return MPREID_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldk * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MPREID_ERR_CUDA; }
+  return MPREID_OK;
+}
+
+template <int PREC>
+static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
+                  int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st) {
+  using C = Cfg<PREC>;
+  constexpr int kpb = ROW_BYTES / C::ELEM;
+  MPREID_REQUIRE(ldk % kpb == 0, "dist_tc: operand planes must be padded to a multiple of %d elements (got %lld)", kpb, (long long)ldk);
+  MPREID_REQUIRE(((uintptr_t)qa & 15) == 0 && ((uintptr_t)ga & 15) == 0, "dist_tc: operands must be 16-byte aligned");
+  Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = make_map(&maps.a_hi, qa, Q, ldk, C::ELEM, BM)) != MPREID_OK) return rc;
+  if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN)) != MPREID_OK) return rc;
+  if (C::PLANES == 2) {
+    if ((rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM)) != MPREID_OK) return rc;
+    if ((rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN)) != MPREID_OK) return rc;
+  }
+  const int m_blocks = (int)ceil_div(Q, BM), n_blocks = (int)ceil_div(G, BN);
+  const int64_t total = (int64_t)m_blocks * n_blocks;
+  MPREID_REQUIRE(total < INT32_MAX, "dist_tc: too many tiles");
+  const int sms = sm_count_of_current_device();
+  const int grid = (int)(total < sms ? total : sms);
+  constexpr int STAGE_BYTES = C::PLANES * (BM + BN) * ROW_BYTES;
+  const int smem = C::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  auto kern = vec ? k_dist_tc<PREC, true> : k_dist_tc<PREC, false>;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, (int)Q, (int)G, (int)(ldk / kpb), metric, out, ld_out, row_max,
+                                    m_blocks, n_blocks);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+}  // namespace tc
+
+int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
+                   int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
+                   float* row_max, cudaStream_t st) {
+  int dev = 0, major = 0;
+  MPREID_CUDA_CHECK(cudaGetDevice(&dev));
+  MPREID_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("dist_tc: the tcgen05 kernels need an sm_100 GPU (found compute capability %d.x)", major);
+    return MPREID_ERR_UNSUPPORTED;
+  }
+  if (precision == MPREID_3XTF32)
+    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, out, ld_out, row_max, st);
+  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, out, ld_out, row_max, st);
+}
+
+}  // namespace mpreid

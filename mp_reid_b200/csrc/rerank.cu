@@ -1,0 +1,535 @@
+// k-reciprocal re-ranking (utils/reranking.py:29-100) as sparse gather kernels.
+//
+// The reference materialises dense N x N fp16 matrices V / V_qe and walks them with three Python
+// loops.  V has at most (k1+1)(round(k1/2)+2) non-zeros per row, so everything here is sparse rows
+// in ELL storage (sorted by column), an inverted index (CSC) over the gallery rows, and one dense
+// pass only where the output itself is dense (the Q x G blend).
+//
+// Orientation: dist[i][j] == reference distmat[j][i]; the reference normalises by the column max and
+// transposes (:46), so row i of `dist` divided by its own max is row i of the reference's
+// original_dist.  Rounding points are the reference's: V and V_qe are fp16, kernel weights are fp32
+// exp / fp32 numpy-pairwise sum, the Jaccard accumulator is fp16, (1-lambda) multiplies in fp16.
+//
+//   k_build_v0      :51-71  k-reciprocal set, 2/3 expansion rule, np.unique, Gaussian kernel row
+//   k_query_expand  :73-78  V_qe[i] = fp16(mean of the V rows of the first k2 neighbours)
+//   k_csc_*         :80-82  inverted index over gallery rows
+//   k_jaccard       :84-99  fp16 min-accumulation in ascending column order, Jaccard, lambda blend
+#include "common.cuh"
+
+namespace mpreid {
+
+static constexpr int kMaxK1 = 100;
+
+HD int v0_capacity(int k1, int64_t N) {
+  const int K1 = k1 + 1, half = round_half_even_div2(k1) + 1;
+  int64_t c = (int64_t)K1 * (1 + half);
+  return (int)(c < N ? c : N);
+}
+HD int64_t v_capacity(int k1, int k2, int64_t N) {
+  if (k2 == 1) return v0_capacity(k1, N);
+  int64_t c = (int64_t)k2 * v0_capacity(k1, N);
+  return c < N ? c : N;
+}
+
+struct RerankWs {
+  float* rowmax;      // [N]
+  int32_t* nbr;       // [N, K]
+  int32_t* v0_col; uint16_t* v0_val; int32_t* v0_len;   // ELL [N, C0]
+  int32_t* v_col;  uint16_t* v_val;  int32_t* v_len;    // ELL [N, C1] (aliases v0 when k2 == 1)
+  int32_t* col_cnt; int32_t* col_fill; int64_t* col_off; // [N], [N], [N+1]
+  int32_t* csc_row; uint16_t* csc_val;                   // [(N-Q) * C1]
+  uint64_t* qe_scratch;                                  // [qe_grid * qe_P]
+  int K, C0; int64_t C1; int qe_grid; int64_t qe_P;
+};
+
+static constexpr int kQeSmemEntries = 4096;
+
+static size_t carve_rerank(RerankWs* w, char* base, int64_t N, int64_t Q, int k1, int k2, int sms) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
+  const int K = (k1 + 1) > k2 ? (k1 + 1) : k2;
+  const int C0 = v0_capacity(k1, N);
+  const int64_t C1 = v_capacity(k1, k2, N);
+  const int qe_grid = sms * 4;
+  int64_t qe_P = 1;
+  while (qe_P < (int64_t)k2 * C0) qe_P <<= 1;
+  if (qe_P <= kQeSmemEntries || k2 == 1) qe_P = 0;  // fits shared memory: no global scratch
+  char* p;
+  p = take(N * 4); if (w) w->rowmax = (float*)p;
+  p = take(N * (size_t)K * 4); if (w) w->nbr = (int32_t*)p;
+  p = take(N * (size_t)C0 * 4); if (w) w->v0_col = (int32_t*)p;
+  p = take(N * (size_t)C0 * 2); if (w) w->v0_val = (uint16_t*)p;
+  p = take(N * 4); if (w) w->v0_len = (int32_t*)p;
+  if (k2 != 1) {
+    p = take(N * (size_t)C1 * 4); if (w) w->v_col = (int32_t*)p;
+    p = take(N * (size_t)C1 * 2); if (w) w->v_val = (uint16_t*)p;
+    p = take(N * 4); if (w) w->v_len = (int32_t*)p;
+  } else if (w) {
+    w->v_col = w->v0_col; w->v_val = w->v0_val; w->v_len = w->v0_len;
+  }
+  p = take(N * 4); if (w) w->col_cnt = (int32_t*)p;
+  p = take(N * 4); if (w) w->col_fill = (int32_t*)p;
+  p = take((N + 1) * 8); if (w) w->col_off = (int64_t*)p;
+  p = take((size_t)(N - Q) * C1 * 4); if (w) w->csc_row = (int32_t*)p;
+  p = take((size_t)(N - Q) * C1 * 2); if (w) w->csc_val = (uint16_t*)p;
+  p = take((size_t)qe_grid * qe_P * 8); if (w) w->qe_scratch = (uint64_t*)p;
+  if (w) { w->K = K; w->C0 = C0; w->C1 = C1; w->qe_grid = qe_grid; w->qe_P = qe_P; }
+  return off;
+}
+
+// numpy float32 pairwise sum (np.sum(weight), utils/reranking.py:71), dense version
+__device__ float pairwise_sum_f32(const float* a, int n) {
+  struct Frame { int lo, n, stage; float left; };
+  Frame st[24];
+  int sp = 1;
+  st[0].lo = 0; st[0].n = n; st[0].stage = 0; st[0].left = 0.f;
+  float ret = 0.f;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.stage == 0) {
+      if (f.n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < f.n; ++i) res += a[f.lo + i];
+        ret = res; --sp; continue;
+      }
+      if (f.n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[f.lo + j];
+        int i = 8;
+        for (; i < f.n - (f.n % 8); i += 8)
+          for (int j = 0; j < 8; ++j) r[j] += a[f.lo + i + j];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < f.n; ++i) res += a[f.lo + i];
+        ret = res; --sp; continue;
+      }
+      int n2 = f.n / 2; n2 -= n2 % 8;
+      f.stage = 1;
+      Frame& c = st[sp++];
+      c.lo = f.lo; c.n = n2; c.stage = 0;
+    } else if (f.stage == 1) {
+      f.left = ret; f.stage = 2;
+      int n2 = f.n / 2; n2 -= n2 % 8;
+      Frame& c = st[sp++];
+      c.lo = f.lo + n2; c.n = f.n - n2; c.stage = 0;
+    } else {
+      ret = f.left + ret; --sp;
+    }
+  }
+  return ret;
+}
+
+template <typename T>
+__device__ __forceinline__ void block_bitonic(T* a, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const T x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exclusive block scan of one int per thread (blockDim.x <= 1024); returns the prefix, total in *total
+__device__ __forceinline__ int block_exclusive_scan(int v, int* sh /*[33]*/, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) sh[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < (int)((blockDim.x + 31) >> 5) ? sh[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    sh[lane] = w;
+  }
+  __syncthreads();
+  const int prefix = (wid > 0 ? sh[wid - 1] : 0) + x - v;
+  *total = sh[((blockDim.x + 31) >> 5) - 1];
+  __syncthreads();
+  return prefix;
+}
+
+// ----------------------------------------------------------------------------------- V0 rows
+static constexpr int kV0Threads = 128;
+static constexpr int kV0MaxK = kMaxK1 + 1;
+static constexpr int kV0MaxHalf = kMaxK1 / 2 + 2;
+static constexpr int kV0ListCap = 8192;  // >= next_pow2((k1+1)(half+1)) for k1 <= 100
+
+struct V0Smem {
+  int32_t fwd[kV0MaxK];
+  int32_t recip[kV0MaxK];
+  int32_t cand_cnt[kV0MaxK], cand_common[kV0MaxK];
+  uint8_t flag[kV0MaxK * kV0MaxHalf];
+  int32_t list[kV0ListCap];
+  float w[kV0MaxK * (kV0MaxHalf + 1)];
+  int32_t n_recip, n_list, n_out;
+  float wsum;
+  int sh[33];
+};
+
+__global__ void __launch_bounds__(kV0Threads)
+k_build_v0(const float* __restrict__ dist, int64_t ld, int N, int k1, int K, int Keff_in,
+           const int32_t* __restrict__ nbr, const float* __restrict__ rowmax,
+           int32_t* __restrict__ v0_col, uint16_t* __restrict__ v0_val, int32_t* __restrict__ v0_len, int C0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V0Smem& s = *reinterpret_cast<V0Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int K1 = min(k1 + 1, Keff_in);                       // forward list length (:53)
+  const int half = min(round_half_even_div2(k1) + 1, Keff_in);  // candidate list length (:60)
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    if (tid == 0) { s.n_recip = 0; s.n_list = 0; }
+    for (int m = tid; m < K1; m += kV0Threads) s.fwd[m] = nbr[(int64_t)i * K + m];
+    __syncthreads();
+    // reciprocity: i in the first K1 neighbours of fwd[m]   (:54-56)
+    for (int m = tid; m < K1; m += kV0Threads) {
+      const int32_t* row = nbr + (int64_t)s.fwd[m] * K;
+      bool hit = false;
+      for (int t = 0; t < K1; ++t) hit |= (row[t] == i);
+      if (hit) { const int p = atomicAdd(&s.n_recip, 1); s.recip[p] = s.fwd[m]; }
+    }
+    __syncthreads();
+    const int nR = s.n_recip;
+    // candidate k-reciprocal sets with the half-size lists  (:58-64)
+    for (int p = tid; p < nR * half; p += kV0Threads) {
+      const int j = p / half, m = p - j * half;
+      const int32_t c = s.recip[j];
+      const int32_t x = nbr[(int64_t)c * K + m];
+      const int32_t* row = nbr + (int64_t)x * K;
+      bool hit = false;
+      for (int t = 0; t < half; ++t) hit |= (row[t] == c);
+      s.flag[j * half + m] = hit ? 1 : 0;
+    }
+    for (int j = tid; j < nR; j += kV0Threads) { s.cand_cnt[j] = 0; s.cand_common[j] = 0; }
+    __syncthreads();
+    for (int p = tid; p < nR * half; p += kV0Threads) {
+      if (!s.flag[p]) continue;
+      const int j = p / half, m = p - j * half;
+      const int32_t x = nbr[(int64_t)s.recip[j] * K + m];
+      bool common = false;
+      for (int t = 0; t < nR; ++t) common |= (s.recip[t] == x);
+      atomicAdd(&s.cand_cnt[j], 1);
+      if (common) atomicAdd(&s.cand_common[j], 1);
+    }
+    __syncthreads();
+    // expansion list = R(i) plus every accepted candidate set  (:65-67), then np.unique (:69)
+    for (int t = tid; t < nR; t += kV0Threads) { const int p = atomicAdd(&s.n_list, 1); s.list[p] = s.recip[t]; }
+    for (int p = tid; p < nR * half; p += kV0Threads) {
+      if (!s.flag[p]) continue;
+      const int j = p / half, m = p - j * half;
+      if ((double)s.cand_common[j] > (2.0 / 3.0) * (double)s.cand_cnt[j]) {
+        const int q = atomicAdd(&s.n_list, 1);
+        s.list[q] = nbr[(int64_t)s.recip[j] * K + m];
+      }
+    }
+    __syncthreads();
+    const int nL = s.n_list;
+    const int P = (int)next_pow2_u32((uint32_t)max(nL, 1));
+    for (int t = nL + tid; t < P; t += kV0Threads) s.list[t] = INT32_MAX;
+    __syncthreads();
+    block_bitonic(s.list, P);
+    // unique -> compact in place (sorted, so compaction keeps order); n_out <= C0
+    if (tid == 0) {
+      int n = 0;
+      for (int t = 0; t < nL; ++t)
+        if (t == 0 || s.list[t] != s.list[t - 1]) s.list[n++] = s.list[t];
+      s.n_out = n;
+    }
+    __syncthreads();
+    const int nU = s.n_out;
+    const float rmax = rowmax[i];
+    const float* drow = dist + (int64_t)i * ld;
+    for (int t = tid; t < nU; t += kV0Threads) {
+      const float dn = drow[s.list[t]] / rmax;          // original_dist[i, idx]  (:46)
+      s.w[t] = (float)exp((double)(-dn));               // np.exp on float32      (:70)
+    }
+    __syncthreads();
+    if (tid == 0) s.wsum = pairwise_sum_f32(s.w, nU);   // np.sum(weight)         (:71)
+    __syncthreads();
+    const float wsum = s.wsum;
+    // V[i, idx] = fp16(weight / sum); entries that underflow to 0 are not stored (V != 0 tests, :82,88)
+    int keep = 0;
+    uint16_t hv = 0;
+    // nU can exceed blockDim: process in rounds, keeping column order
+    int written = 0;
+    for (int t0 = 0; t0 < nU; t0 += kV0Threads) {
+      const int t = t0 + tid;
+      keep = 0;
+      if (t < nU) {
+        const __half h = __float2half_rn(s.w[t] / wsum);
+        hv = __half_as_ushort(h);
+        keep = (hv & 0x7fff) != 0;
+      }
+      int total;
+      const int pos = block_exclusive_scan(keep, s.sh, &total);
+      if (keep) {
+        v0_col[(int64_t)i * C0 + written + pos] = s.list[t];
+        v0_val[(int64_t)i * C0 + written + pos] = hv;
+      }
+      written += total;
+    }
+    if (tid == 0) v0_len[i] = written;
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------- query expansion
+static constexpr int kQeThreads = 256;
+
+__global__ void __launch_bounds__(kQeThreads)
+k_query_expand(int N, int K, int k2, const int32_t* __restrict__ nbr,
+               const int32_t* __restrict__ v0_col, const uint16_t* __restrict__ v0_val, const int32_t* __restrict__ v0_len, int C0,
+               int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1,
+               uint64_t* __restrict__ scratch, int64_t scratch_P) {
+  __shared__ uint64_t sbuf[kQeSmemEntries];
+  __shared__ int sh[33];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  const float inv_cnt = (float)k2;
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    // gather (col, m, val) of the k2 neighbour rows; key = col<<32 | m<<16 | fp16 bits
+    if (tid == 0) {
+      int t = 0;
+      for (int m = 0; m < k2; ++m) {
+        const int32_t r = nbr[(int64_t)i * K + m];
+        t += r >= 0 ? v0_len[r] : 0;
+      }
+      s_total = t;
+    }
+    __syncthreads();
+    const int T = s_total;
+    const int P = (int)next_pow2_u32((uint32_t)max(T, 1));
+    uint64_t* buf = (P <= kQeSmemEntries) ? sbuf : scratch + (int64_t)blockIdx.x * scratch_P;
+    {
+      int base = 0;
+      for (int m = 0; m < k2; ++m) {
+        const int32_t r = nbr[(int64_t)i * K + m];
+        const int len = r >= 0 ? v0_len[r] : 0;
+        for (int e = tid; e < len; e += kQeThreads) {
+          const uint64_t col = (uint32_t)v0_col[(int64_t)r * C0 + e];
+          buf[base + e] = (col << 32) | ((uint64_t)m << 16) | v0_val[(int64_t)r * C0 + e];
+        }
+        base += len;
+      }
+      for (int t = T + tid; t < P; t += kQeThreads) buf[t] = ~0ull;
+    }
+    __syncthreads();
+    block_bitonic(buf, P);
+    // segment heads sum their (<= k2) members in m order, fp32, then / k2 -> fp16   (:76)
+    int written = 0;
+    for (int t0 = 0; t0 < T; t0 += kQeThreads) {
+      const int t = t0 + tid;
+      int keep = 0;
+      uint16_t hv = 0;
+      int32_t col = 0;
+      if (t < T) {
+        const uint64_t key = buf[t];
+        col = (int32_t)(key >> 32);
+        const bool head = (t == 0) || ((int32_t)(buf[t - 1] >> 32) != col);
+        if (head) {
+          float sum = __half2float(__ushort_as_half((uint16_t)(key & 0xffff)));
+          for (int u = t + 1; u < T && (int32_t)(buf[u] >> 32) == col; ++u)
+            sum += __half2float(__ushort_as_half((uint16_t)(buf[u] & 0xffff)));
+          hv = __half_as_ushort(__float2half_rn(sum / inv_cnt));
+          keep = (hv & 0x7fff) != 0;
+        }
+      }
+      int total;
+      const int pos = block_exclusive_scan(keep, sh, &total);
+      if (keep) {
+        v_col[(int64_t)i * C1 + written + pos] = col;
+        v_val[(int64_t)i * C1 + written + pos] = hv;
+      }
+      written += total;
+    }
+    if (tid == 0) v_len[i] = written;
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------- inverted index
+__global__ void k_zero_i32(int32_t* a, int32_t* b, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = 0; b[i] = 0; }
+}
+
+__global__ void k_csc_count(int N, int Q, const int32_t* __restrict__ v_col, const int32_t* __restrict__ v_len, int64_t C1,
+                            int32_t* col_cnt) {
+  // one warp per gallery row
+  const int g = Q + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (g >= N) return;
+  const int len = v_len[g];
+  for (int e = threadIdx.x & 31; e < len; e += 32) atomicAdd(&col_cnt[v_col[(int64_t)g * C1 + e]], 1);
+}
+
+__global__ void k_scan_i64(const int32_t* __restrict__ in, int64_t* out, int64_t n) {
+  __shared__ int64_t warp_sums[32];
+  __shared__ int64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += blockDim.x) {
+    const int64_t i = base + tid;
+    const int64_t v = i < n ? in[i] : 0;
+    int64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int64_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    if (i < n) out[i] = carry_s + (wid > 0 ? warp_sums[wid - 1] : 0) + x - v;
+    __syncthreads();
+    if (tid == 0) carry_s += warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry_s;
+}
+
+__global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val,
+                           const int32_t* __restrict__ v_len, int64_t C1, const int64_t* __restrict__ col_off,
+                           int32_t* col_fill, int32_t* __restrict__ csc_row, uint16_t* __restrict__ csc_val) {
+  const int g = Q + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (g >= N) return;
+  const int len = v_len[g];
+  for (int e = threadIdx.x & 31; e < len; e += 32) {
+    const int32_t c = v_col[(int64_t)g * C1 + e];
+    const int64_t p = col_off[c] + atomicAdd(&col_fill[c], 1);
+    csc_row[p] = g;
+    csc_val[p] = v_val[(int64_t)g * C1 + e];
+  }
+}
+
+// ----------------------------------------------------------------------------------- Jaccard + blend
+static constexpr int kJacThreads = 512;
+
+__global__ void __launch_bounds__(kJacThreads)
+k_jaccard(const float* __restrict__ dist, int64_t ld, int N, int Q, float lambda_value,
+          const float* __restrict__ rowmax,
+          const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
+          const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
+          float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* acc = reinterpret_cast<__half*>(smem_raw);  // [tile_cols] fp16 accumulator (temp_min, :87)
+  const int tid = threadIdx.x;
+  const int G = N - Q;
+  const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
+  const __half h_one = __float2half_rn(1.f), h_two = __float2half_rn(2.f);
+  for (int i = blockIdx.x; i < Q; i += gridDim.x) {
+    const int len = v_len[i];
+    const float rmax = rowmax[i];
+    const float* drow = dist + (int64_t)i * ld + Q;
+    float* orow = final_dist + (int64_t)i * ld_final;
+    for (int t0 = 0; t0 < G; t0 += tile_cols) {
+      const int tn = min(tile_cols, G - t0);
+      for (int c = tid; c < tn; c += kJacThreads) acc[c] = __float2half_rn(0.f);
+      __syncthreads();
+      for (int e = 0; e < len; ++e) {           // ascending column k: the reference's accumulation order (:88-92)
+        const int32_t k = v_col[(int64_t)i * C1 + e];
+        const __half vik = __ushort_as_half(v_val[(int64_t)i * C1 + e]);
+        const int64_t b = col_off[k], n = col_off[k + 1] - b;
+        for (int64_t u = tid; u < n; u += kJacThreads) {
+          const int c = csc_row[b + u] - Q - t0;
+          if (c >= 0 && c < tn) {
+            const __half vg = __ushort_as_half(csc_val[b + u]);
+            const __half mn = __hlt(vg, vik) ? vg : vik;
+            acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+          }
+        }
+        __syncthreads();
+      }
+      for (int c = tid; c < tn; c += kJacThreads) {
+        const float a = __half2float(acc[c]);
+        const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
+        const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
+        const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
+        const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
+        const float dn = drow[t0 + c] / rmax;                                    // original_dist[i, Q+g]   (:46,72)
+        orow[t0 + c] = __half2float(jl) + dn * lambda_value;                     // (:95)
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace mpreid
+
+using namespace mpreid;
+
+extern "C" size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, int k2) {
+  if (N <= 0 || Q <= 0 || Q >= N || k1 < 1 || k1 > kMaxK1 || k2 < 1) return 0;
+  return carve_rerank(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
+}
+
+extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, int64_t N, int64_t Q, int k1, int k2, float lambda_value,
+                             float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
+                             int32_t* status, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MPREID_REQUIRE(dist && final_dist && workspace, "rerank: null pointer");
+  MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && N < INT32_MAX && ld_dist >= N && ld_final >= N - Q, "rerank: bad shape N=%lld Q=%lld",
+                 (long long)N, (long long)Q);
+  MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1, "rerank: k1 must be in [1, %d]", kMaxK1);
+  MPREID_REQUIRE(k2 >= 1 && k2 <= 64, "rerank: k2 must be in [1, 64]");
+  MPREID_REQUIRE(((uintptr_t)workspace & 255) == 0, "rerank: workspace must be 256-byte aligned");
+  const int sms = sm_count_of_current_device();
+  if (workspace_bytes < carve_rerank(nullptr, nullptr, N, Q, k1, k2, sms)) {
+    set_error("rerank: workspace too small (%zu bytes)", workspace_bytes);
+    return MPREID_ERR_WORKSPACE;
+  }
+  RerankWs w;
+  carve_rerank(&w, (char*)workspace, N, Q, k1, k2, sms);
+  const int Keff = (int)(w.K < N ? w.K : N);
+  int rc;
+  // :46-48  row max (== the reference's column max in this orientation) and the first K neighbours
+  if ((rc = mpreid_row_max(dist, ld_dist, N, N, w.rowmax, stream)) != MPREID_OK) return rc;
+  if ((rc = mpreid_row_topk(dist, ld_dist, N, N, w.K, w.rowmax, w.nbr, nullptr, stream)) != MPREID_OK) return rc;
+  // :51-71
+  static bool attr_v0 = false, attr_jac = false;
+  const int v0_smem = (int)sizeof(V0Smem);
+  if (!attr_v0) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
+    attr_v0 = true;
+  }
+  const int64_t v0_grid = N < (int64_t)sms * 16 ? N : (int64_t)sms * 16;
+  k_build_v0<<<(unsigned)v0_grid, kV0Threads, v0_smem, st>>>(dist, ld_dist, (int)N, k1, w.K, Keff, w.nbr, w.rowmax,
+                                                             w.v0_col, w.v0_val, w.v0_len, w.C0);
+  // :73-78
+  if (k2 != 1) {
+    const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
+    k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, w.K, k2 < Keff ? k2 : Keff, w.nbr, w.v0_col, w.v0_val,
+                                                             w.v0_len, w.C0, w.v_col, w.v_val, w.v_len, w.C1,
+                                                             w.qe_scratch, w.qe_P);
+  }
+  // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
+  k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
+  const int rows_per_cta = 8;
+  const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
+  k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, w.v_col, w.v_len, w.C1, w.col_cnt);
+  k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
+  k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, w.v_col, w.v_val, w.v_len, w.C1, w.col_off, w.col_fill,
+                                                     w.csc_row, w.csc_val);
+  // :84-99
+  const int64_t G = N - Q;
+  int tile_cols = (int)(G < 100 * 1024 ? G : 100 * 1024);
+  tile_cols = (tile_cols + 7) & ~7;
+  const int jac_smem = tile_cols * 2;
+  if (!attr_jac) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 * 2));
+    attr_jac = true;
+  }
+  const int ctas_per_sm = jac_smem <= 48 * 1024 ? 4 : (jac_smem <= 100 * 1024 ? 2 : 1);
+  const int64_t jac_grid = Q < (int64_t)sms * ctas_per_sm ? Q : (int64_t)sms * ctas_per_sm;
+  k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist, ld_dist, (int)N, (int)Q, lambda_value, w.rowmax, w.v_col, w.v_val,
+                                                               w.v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist, ld_final,
+                                                               tile_cols);
+  if (status) MPREID_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}

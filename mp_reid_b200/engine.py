@@ -1,0 +1,243 @@
+"""Device-side engine: thin, typed wrappers over the C ABI working on torch CUDA tensors.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only.  Every function
+launches on torch's current stream and never synchronises unless it says so.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mp_reid_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+
+
+def default_precision() -> str:
+    return os.environ.get("MPREID_PRECISION", "3xtf32").lower()
+
+
+def default_junk() -> str:
+    return os.environ.get("MPREID_JUNK", "none").lower()
+
+
+@dataclass
+class Prepared:
+    """Feature rows ready for the distance kernels (all on one device)."""
+    n: int
+    D: int
+    Dp: int
+    xn: torch.Tensor | None      # [n, D] fp32 (normalised or raw copy)
+    sqnorm: torch.Tensor         # [n]
+    norm: torch.Tensor           # [n]
+    hi: torch.Tensor | None      # [n, Dp] fp32 (TF32-exact)
+    lo: torch.Tensor | None
+    bf: torch.Tensor | None      # [n, Dp] bf16
+
+    def rows(self, a: int, b: int) -> "Prepared":
+        s = lambda t: None if t is None else t[a:b]
+        return Prepared(b - a, self.D, self.Dp, s(self.xn), self.sqnorm[a:b], self.norm[a:b], s(self.hi), s(self.lo), s(self.bf))
+
+
+def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, keep_xn: bool = True) -> Prepared:
+    """F.normalize + squared norms + operand planes in one pass (utils/metrics.py:10-11,114)."""
+    require_cuda()
+    lib = L.load()
+    precision = (precision or default_precision()).lower()
+    prec = L.PRECISIONS[precision]
+    assert x.is_cuda and x.dim() == 2
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, D = x.shape
+    dev = x.device
+    pad = 64 if prec == L.BF16 else 32
+    Dp = (D + pad - 1) // pad * pad
+    need_xn = keep_xn or prec == L.FP32_SIMT
+    xn = torch.empty((n, D), dtype=torch.float32, device=dev) if need_xn else None
+    sqnorm = torch.empty((n,), dtype=torch.float32, device=dev)
+    norm = torch.empty((n,), dtype=torch.float32, device=dev)
+    hi = lo = bf = None
+    if prec == L.X3TF32:
+        hi = torch.empty((n, Dp), dtype=torch.float32, device=dev)
+        lo = torch.empty((n, Dp), dtype=torch.float32, device=dev)
+    elif prec == L.BF16:
+        bf = torch.empty((n, Dp), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_prep_rows(x.data_ptr(), n, D, x.stride(0), int(bool(normalize)), _ptr(xn), D, sqnorm.data_ptr(),
+                                     norm.data_ptr(), _ptr(hi), _ptr(lo), _ptr(bf), Dp, _stream()), "prep_rows")
+    return Prepared(n, D, Dp, xn, sqnorm, norm, hi, lo, bf)
+
+
+def alloc_dist(Q: int, G: int, device) -> torch.Tensor:
+    """[Q, G] fp32 view over a buffer whose leading dimension is padded to 128 B (vector stores, TMA)."""
+    ld = (G + 31) // 32 * 32
+    return torch.empty((Q, ld), dtype=torch.float32, device=device)[:, :G]
+
+
+def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: str | None = None,
+                out: torch.Tensor | None = None, row_max: torch.Tensor | None = None) -> torch.Tensor:
+    """utils/metrics.py:7-25, processor_uniprompt_stage2.py:466-468, utils/reranking.py:36-41."""
+    require_cuda()
+    lib = L.load()
+    precision = (precision or default_precision()).lower()
+    prec, met = L.PRECISIONS[precision], L.METRICS[metric]
+    dev = q.sqnorm.device
+    if out is None:
+        out = alloc_dist(q.n, g.n, dev)
+    assert out.shape == (q.n, g.n) and out.stride(1) == 1 and out.dtype == torch.float32
+    if met == L.ARCCOS:
+        qa, ga = q.norm, g.norm
+    elif met == L.ONE_MINUS_DOT:
+        qa = ga = None
+    else:
+        qa, ga = q.sqnorm, g.sqnorm
+    if prec == L.FP32_SIMT:
+        if q.xn is None or g.xn is None or g.xn.stride(0) != q.xn.stride(0):
+            raise ValueError("SIMT path needs the fp32 rows of both sides with equal leading dimensions")
+        a, b, c, d, K, ldk = q.xn, None, g.xn, None, q.D, q.xn.stride(0)
+    elif prec == L.X3TF32:
+        a, b, c, d, K, ldk = q.hi, q.lo, g.hi, g.lo, q.Dp, q.Dp
+    else:
+        a, b, c, d, K, ldk = q.bf, None, g.bf, None, q.Dp, q.Dp
+    if a is None or c is None:
+        raise ValueError(f"features were not prepared for precision '{precision}'")
+    if row_max is not None:
+        row_max.fill_(float("-inf"))
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_dist_matrix(_ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(qa), _ptr(ga), q.n, g.n, K, ldk, met, prec,
+                                       out.data_ptr(), out.stride(0), _ptr(row_max), _stream()), "dist_matrix")
+    return out
+
+
+def _labels(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int64, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int64)).to(device, non_blocking=True)
+
+
+_pos_capacity_hint = {}
+
+
+def rank_eval(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: str | None = None):
+    """eval_func's per-query part (utils/metrics.py:39-80) -> (first_hit i32[Q], ap f64[Q], num_rel i32[Q]) on device.
+
+    Synchronises once (to read the 16-byte status word that tells whether the positives workspace
+    was large enough; it is re-run with the exact size otherwise).
+    """
+    require_cuda()
+    lib = L.load()
+    junk_mode = L.JUNKS[(junk or default_junk()).lower()]
+    assert dist.is_cuda and dist.dtype == torch.float32 and dist.stride(1) == 1
+    Q, G = dist.shape
+    dev = dist.device
+    q_pid, g_pid = _labels(q_pid, dev), _labels(g_pid, dev)
+    if junk_mode != L.JUNK_NONE:
+        q_cam, g_cam = _labels(q_cam, dev), _labels(g_cam, dev)
+    else:
+        q_cam = g_cam = None
+    first_hit = torch.empty((Q,), dtype=torch.int32, device=dev)
+    ap = torch.empty((Q,), dtype=torch.float64, device=dev)
+    num_rel = torch.empty((Q,), dtype=torch.int32, device=dev)
+    status = torch.zeros((4,), dtype=torch.int32, device=dev)
+    cap = max(_pos_capacity_hint.get((Q, G), 0), 64 * Q, 1 << 16)
+    for attempt in range(2):
+        nbytes = lib.mpreid_rank_eval_workspace_bytes(Q, G, cap)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.mpreid_rank_eval(dist.data_ptr(), dist.stride(0), Q, G, q_pid.data_ptr(), g_pid.data_ptr(),
+                                         _ptr(q_cam), _ptr(g_cam), junk_mode, first_hit.data_ptr(), ap.data_ptr(),
+                                         num_rel.data_ptr(), ws.data_ptr(), nbytes, cap, status.data_ptr(), _stream()),
+                    "rank_eval")
+        st = status.cpu()
+        if int(st[0]) == 0:
+            break
+        need = int(st[1])
+        if need >= 2**31 - 1:
+            raise L.MpreidError("rank_eval: more than 2^31 same-pid (query, gallery) pairs")
+        cap = need
+        _pos_capacity_hint[(Q, G)] = need
+    else:
+        raise L.MpreidError("rank_eval: positives workspace overflow after resize")
+    return first_hit, ap, num_rel
+
+
+def reduce_cmc_map(first_hit, ap, num_rel, max_rank: int, num_g: int, denominators: str = "valid"):
+    """utils/metrics.py:82-86 on the gathered per-query values, computed by numpy itself.
+
+    denominators='valid' is eval_func; 'all' is the inline CLIP-style loop
+    (processor/processor_uniprompt_stage2.py:508-509: mean over all queries, float64 CMC).
+    """
+    first_hit = np.asarray(first_hit)
+    ap = np.asarray(ap, dtype=np.float64)
+    num_rel = np.asarray(num_rel)
+    valid = num_rel > 0
+    n_valid = float(valid.sum())
+    assert n_valid > 0, "Error: all query identities do not appear in gallery"
+    fh = first_hit[valid].astype(np.int64)
+    counts = np.bincount(np.minimum(fh, max_rank + 1), minlength=max_rank + 2)[1:max_rank + 1].cumsum()
+    if denominators == "valid":
+        cmc = counts.astype(np.float32) / n_valid
+        mAP = np.mean(ap[valid])
+    else:
+        cmc = counts.astype(np.float64) / len(first_hit)
+        mAP = np.where(valid, ap, 0.0).mean()
+    return cmc, mAP
+
+
+def row_topk(dist: torch.Tensor, k: int, row_scale: torch.Tensor | None = None, want_values: bool = False):
+    require_cuda()
+    lib = L.load()
+    Q, G = dist.shape
+    idx = torch.empty((Q, k), dtype=torch.int32, device=dist.device)
+    val = torch.empty((Q, k), dtype=torch.float32, device=dist.device) if want_values else None
+    with torch.cuda.device(dist.device):
+        L.check(lib.mpreid_row_topk(dist.data_ptr(), dist.stride(0), Q, G, k, _ptr(row_scale), idx.data_ptr(), _ptr(val), _stream()),
+                "row_topk")
+    return (idx, val) if want_values else idx
+
+
+def row_max(dist: torch.Tensor) -> torch.Tensor:
+    require_cuda()
+    lib = L.load()
+    Q, G = dist.shape
+    out = torch.empty((Q,), dtype=torch.float32, device=dist.device)
+    with torch.cuda.device(dist.device):
+        L.check(lib.mpreid_row_max(dist.data_ptr(), dist.stride(0), Q, G, out.data_ptr(), _stream()), "row_max")
+    return out
+
+
+def rerank_from_dist(dist_all: torch.Tensor, query_num: int, k1: int, k2: int, lambda_value: float,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """utils/reranking.py:45-99 on an all-pairs matrix in the orientation dist_all[i][j] = distmat[j][i]."""
+    require_cuda()
+    lib = L.load()
+    N = dist_all.shape[0]
+    assert dist_all.shape == (N, N) and dist_all.stride(1) == 1 and dist_all.dtype == torch.float32
+    dev = dist_all.device
+    G = N - query_num
+    if out is None:
+        out = alloc_dist(query_num, G, dev)
+    nbytes = lib.mpreid_rerank_workspace_bytes(N, query_num, k1, k2)
+    if nbytes == 0:
+        raise ValueError(f"re_ranking: unsupported arguments N={N} Q={query_num} k1={k1} k2={k2}")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_rerank(dist_all.data_ptr(), dist_all.stride(0), N, query_num, k1, k2, float(lambda_value),
+                                  out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, None, _stream()), "rerank")
+    return out

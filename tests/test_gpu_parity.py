@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+reference outputs (tests/golden, produced by the unmodified reference via oracle/make_golden.py).
+
+Bars: integer / index work and CMC / AP / mAP on a GIVEN distance matrix are
+bit-exact; distances are within 1e-4 * (|q|^2 + |g|^2) in the fp32-accurate mode; re-ranked mAP
+within 1e-4.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mp_reid_b200 import engine as E
+from mp_reid_b200 import metrics, reranking, synth
+from oracle import mpreid_oracle as orc
+
+CASES = ["small_eval", "ties_eval", "small_gallery", "no_match", "rerank_small", "cctv_small"]
+DEV = "cuda:0"
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV, dtype=dtype)
+
+
+def norm_feats(g):
+    qf, gf = g["qf"], g["gf"]
+    if bool(g["normalize"]):
+        allf = orc.l2_normalize(np.concatenate([qf, gf]))
+        return allf[: len(qf)], allf[len(qf):]
+    return qf, gf
+
+
+def dist_tol(qn, gn):
+    return 1e-4 * ((qn.astype(np.float64) ** 2).sum(1)[:, None] + (gn.astype(np.float64) ** 2).sum(1)[None, :])
+
+
+# ------------------------------------------------------------------------------------ prep
+def test_prep_rows_normalise_norms_and_planes():
+    torch.manual_seed(0)
+    x = torch.randn(300, 1280, device=DEV) * 3
+    for prec in ["3xtf32", "bf16", "simt"]:
+        p = E.prep_rows(x, normalize=True, precision=prec)
+        ref = torch.nn.functional.normalize(x, dim=1, p=2)
+        assert torch.allclose(p.xn, ref, rtol=0, atol=2e-7)
+        assert torch.allclose(p.sqnorm, (ref * ref).sum(1), rtol=0, atol=1e-6)
+        assert torch.allclose(p.norm, p.sqnorm.sqrt(), rtol=0, atol=1e-6)
+        if prec == "3xtf32":
+            assert p.hi.shape == (300, 1280)
+            assert torch.all((p.hi.view(torch.int32) & 0x1FFF) == 0) and torch.all((p.lo.view(torch.int32) & 0x1FFF) == 0)
+            assert torch.allclose(p.hi + p.lo, p.xn, rtol=0, atol=1e-9 + 2.0 ** -21 * float(p.xn.abs().max()))
+        if prec == "bf16":
+            assert torch.equal(p.bf[:, :1280], p.xn.to(torch.bfloat16))
+    # ragged D: zero padding up to the TMA box
+    y = torch.randn(7, 100, device=DEV)
+    p = E.prep_rows(y, normalize=False, precision="3xtf32")
+    assert p.Dp == 128 and torch.all(p.hi[:, 100:] == 0) and torch.all(p.lo[:, 100:] == 0)
+    assert torch.equal(p.xn, y)
+
+
+# ------------------------------------------------------------------------------------ distances
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("prec", ["simt", "3xtf32", "bf16"])
+def test_distances_vs_reference(golden_dir, name, prec):
+    g = load(golden_dir, name)
+    qn, gn = norm_feats(g)
+    tol = dist_tol(qn, gn)
+    scale = 1.0 if prec != "bf16" else 60.0   # bf16 operands: ~2^-8 relative per product, stated path
+    d = metrics.euclidean_distance(torch.from_numpy(qn), torch.from_numpy(gn), precision=prec)
+    assert d.dtype == np.float32 and d.shape == g["dist_euclid"].shape
+    assert np.all(np.abs(d.astype(np.float64) - g["dist_euclid"]) <= scale * tol), np.abs(d - g["dist_euclid"]).max()
+    d1 = metrics.one_minus_cosine(torch.from_numpy(qn), torch.from_numpy(gn), precision=prec)
+    assert np.all(np.abs(d1.astype(np.float64) - g["dist_1mcos"]) <= scale * tol)
+    if bool(g["normalize"]):
+        da = metrics.cosine_similarity(torch.from_numpy(qn), torch.from_numpy(gn), precision=prec)
+        # d(arccos)/dx reaches 224 at the clip points: compare cosines, and angles loosely
+        assert np.all(np.abs(np.cos(da.astype(np.float64)) - np.cos(g["dist_arccos"].astype(np.float64))) <= scale * 2e-4)
+        assert np.abs(da - g["dist_arccos"]).max() <= (5e-3 if prec != "bf16" else 0.2)
+
+
+def test_tcgen05_matches_simt_on_ragged_tiles():
+    # shapes that are not multiples of the 128 x 256 tile nor of the 32-wide k block
+    torch.manual_seed(1)
+    for (Q, G, D) in [(1, 1, 8), (130, 257, 100), (129, 1000, 1280), (300, 513, 33)]:
+        q = torch.randn(Q, D, device=DEV)
+        g = torch.randn(G, D, device=DEV)
+        ref = (q.double() ** 2).sum(1)[:, None] + (g.double() ** 2).sum(1)[None] - 2 * q.double() @ g.double().T
+        for prec, rel in [("simt", 2e-6), ("3xtf32", 4e-6), ("bf16", 2e-2)]:
+            pq = E.prep_rows(q, False, prec)
+            pg = E.prep_rows(g, False, prec)
+            rm = torch.empty(Q, device=DEV)
+            d = E.dist_matrix(pq, pg, "sqeuclid", prec, row_max=rm)
+            bound = rel * ((q.double() ** 2).sum(1)[:, None] + (g.double() ** 2).sum(1)[None])
+            assert torch.all((d.double() - ref).abs() <= bound), (Q, G, D, prec, float((d.double() - ref).abs().max()))
+            assert torch.equal(rm, d.max(dim=1).values), (Q, G, D, prec)
+
+
+# ------------------------------------------------------------------------------------ rank + CMC/AP
+@pytest.mark.parametrize("name", CASES)
+def test_rank_eval_bit_exact_on_reference_distmat(golden_dir, name):
+    g = load(golden_dir, name)
+    args = (g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
+    for dkey in ["dist_euclid", "dist_1mcos"]:
+        for junk in ["none", "pid_cam"]:
+            want = None
+            try:
+                want = orc.rank_eval(g[dkey], *args, sort_kind="stable", junk=junk)
+            except (AssertionError, ValueError):
+                want = None  # reference cannot stack ragged junk-filtered rows when G < max_rank
+            fh, ap, nr = E.rank_eval(dev(g[dkey]), *args, junk=junk)
+            fh, ap, nr = fh.cpu().numpy(), ap.cpu().numpy(), nr.cpu().numpy()
+            if want is not None:
+                assert np.array_equal(fh, want["first_hit"]), (name, dkey, junk)
+                assert np.array_equal(nr, want["num_rel"])
+                assert np.array_equal(ap, want["ap"]), (name, dkey, junk, np.abs(ap - want["ap"]).max())
+    cmc, mAP = metrics.eval_func(g["dist_euclid"], *args)
+    assert cmc.dtype == np.float32 and np.array_equal(cmc, g["ref_stable_cmc"])
+    assert mAP == g["ref_stable_mAP"]
+    assert abs(mAP - g["ref_mAP"]) <= (1e-6 if name != "ties_eval" else 5e-2)   # unmodified reference: unstable tie order
+    if "ref_junk_mAP" in g:
+        cmc, mAP = metrics.eval_func(g["dist_euclid"], *args, junk="pid_cam")
+        assert np.array_equal(cmc, g["ref_junk_cmc"]) and mAP == g["ref_junk_mAP"]
+    cmc, mAP = metrics.clipstyle_eval(g["dist_1mcos"], *args)
+    assert np.array_equal(cmc, g["ref_clip_cmc"]) and mAP == g["ref_clip_mAP"]
+
+
+def test_rank_eval_random_medium_with_ties_and_odd_alignment():
+    rng = np.random.RandomState(3)
+    for (Q, G, n_id, quant) in [(257, 4099, 40, None), (64, 20001, 7, 64), (33, 515, 3, 4), (5, 1, 1, None)]:
+        d = rng.rand(Q, G).astype(np.float32)
+        if quant:
+            d = np.round(d * quant).astype(np.float32) / quant   # heavy exact ties
+        q_pid, g_pid = rng.randint(0, n_id, Q), rng.randint(0, n_id, G)
+        q_cam, g_cam = rng.randint(0, 3, Q), rng.randint(0, 3, G)
+        q_pid[0] = 999  # a query without any match
+        for junk in ["none", "pid_cam"]:
+            try:
+                want = orc.rank_eval(d, q_pid, g_pid, q_cam, g_cam, junk=junk)
+            except (AssertionError, ValueError):
+                continue
+            fh, ap, nr = E.rank_eval(dev(d), q_pid, g_pid, q_cam, g_cam, junk=junk)
+            assert np.array_equal(fh.cpu().numpy(), want["first_hit"]), (Q, G, junk)
+            assert np.array_equal(nr.cpu().numpy(), want["num_rel"])
+            assert np.array_equal(ap.cpu().numpy(), want["ap"])
+
+
+def test_rank_eval_many_positives_per_query():
+    # one identity owns most of the gallery: more same-pid entries than one shared-memory pass holds
+    rng = np.random.RandomState(4)
+    Q, G = 6, 9000
+    d = rng.rand(Q, G).astype(np.float32)
+    g_pid = np.zeros(G, np.int64); g_pid[::9] = 1
+    q_pid = np.array([0, 0, 1, 0, 1, 0])
+    q_cam, g_cam = rng.randint(0, 2, Q), rng.randint(0, 2, G)
+    for junk in ["none", "pid_cam"]:
+        want = orc.rank_eval(d, q_pid, g_pid, q_cam, g_cam, junk=junk)
+        fh, ap, nr = E.rank_eval(dev(d), q_pid, g_pid, q_cam, g_cam, junk=junk)
+        assert np.array_equal(fh.cpu().numpy(), want["first_hit"])
+        assert np.array_equal(nr.cpu().numpy(), want["num_rel"])
+        assert np.array_equal(ap.cpu().numpy(), want["ap"])
+
+
+def test_eval_func_error_and_note_conventions(capsys):
+    d = np.random.RandomState(0).rand(3, 10).astype(np.float32)
+    with pytest.raises(AssertionError, match="all query identities do not appear in gallery"):
+        metrics.eval_func(d, np.array([1, 2, 3]), np.arange(10) + 10, np.zeros(3, int), np.zeros(10, int))
+    cmc, _ = metrics.eval_func(d, np.array([1, 2, 3]), np.array([1, 2, 3] * 3 + [1]), np.zeros(3, int), np.zeros(10, int))
+    assert cmc.shape == (10,) and "quite small" in capsys.readouterr().out
+
+
+# ------------------------------------------------------------------------------------ top-k
+def test_row_topk_equals_stable_argsort_prefix():
+    rng = np.random.RandomState(5)
+    for (Q, G, k, quant, scaled) in [(50, 5000, 21, None, True), (20, 30000, 100, 128, True), (9, 37, 51, 8, False),
+                                      (3, 100003, 51, None, True), (4, 2500, 1000, 16, True)]:
+        d = (rng.rand(Q, G).astype(np.float32) + 0.25)
+        if quant:
+            d = np.round(d * quant).astype(np.float32) / quant
+        scale = d.max(1).astype(np.float32) if scaled else None
+        dn = (d / scale[:, None]).astype(np.float32) if scaled else d
+        want = np.argsort(dn, axis=1, kind="stable")[:, :k]
+        idx, val = E.row_topk(dev(d), k, dev(scale) if scaled else None, want_values=True)
+        idx, val = idx.cpu().numpy(), val.cpu().numpy()
+        kk = min(k, G)
+        assert np.array_equal(idx[:, :kk], want), (Q, G, k)
+        assert np.array_equal(val[:, :kk], np.take_along_axis(dn, want, 1))
+        assert np.all(idx[:, kk:] == -1)
+    rm = E.row_max(dev(d)).cpu().numpy()
+    assert np.array_equal(rm, d.max(1))
+
+
+# ------------------------------------------------------------------------------------ re-ranking
+@pytest.mark.parametrize("name,params", [("small_eval", [(6, 3, 0.3), (10, 1, 0.3)]),
+                                         ("rerank_small", [(20, 6, 0.3), (50, 15, 0.3), (7, 2, 0.5)])])
+def test_rerank_sparse_stages_on_reference_all_pairs_matrix(golden_dir, name, params):
+    """Given the SAME all-pairs matrix the reference computes (oracle sgemm), the sparse pipeline
+    must reproduce final_dist: exactly, up to fp16-ulp flips caused by exp() last-bit differences."""
+    g = load(golden_dir, name)
+    qn, gn = norm_feats(g)
+    nq = len(qn)
+    dall = orc.pairwise_sq_all(np.concatenate([qn, gn]).astype(np.float32))
+    for (k1, k2, lam) in params:
+        tag = f"rr_{k1}_{k2}_{int(lam * 100)}"
+        want = g[tag + "_final"]
+        got = E.rerank_from_dist(dev(dall.T.copy()), nq, k1, k2, lam).cpu().numpy()
+        diff = np.abs(got - want)
+        frac_exact = float((diff == 0).mean())
+        assert diff.max() <= 2e-3, (tag, diff.max())
+        assert frac_exact >= 0.99, (tag, frac_exact)
+        r = orc.rank_eval(got, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
+        assert abs(r["mAP"] - g[tag + "_mAP"]) <= 1e-4
+
+
+@pytest.mark.parametrize("prec,tol", [("3xtf32", 1e-4), ("bf16", 5e-3)])
+def test_re_ranking_api_end_to_end(golden_dir, prec, tol):
+    g = load(golden_dir, "rerank_small")
+    qn, gn = norm_feats(g)
+    for (k1, k2, lam) in [(20, 6, 0.3), (50, 15, 0.3)]:
+        tag = f"rr_{k1}_{k2}_{int(lam * 100)}"
+        fd = reranking.re_ranking(torch.from_numpy(qn), torch.from_numpy(gn), k1, k2, lam, precision=prec)
+        assert fd.dtype == np.float32 and fd.shape == g[tag + "_final"].shape
+        cmc, mAP = metrics.eval_func(fd, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
+        assert abs(mAP - g[tag + "_mAP"]) <= tol, (tag, mAP, g[tag + "_mAP"])
+
+
+# ------------------------------------------------------------------------------------ evaluator object
+@pytest.mark.parametrize("name", ["small_eval", "cctv_small", "no_match"])
+def test_evaluator_drop_in_sequence(golden_dir, name, capsys):
+    g = load(golden_dir, name)
+    ev = metrics.R1_mAP_eval(len(g["qf"]), max_rank=50, feat_norm="yes")   # cfg.TEST.FEAT_NORM is the string 'yes'
+    ev.reset()
+    allf = np.concatenate([g["qf"], g["gf"]])
+    pids = np.concatenate([g["q_pid"], g["g_pid"]])
+    cams = np.concatenate([g["q_cam"], g["g_cam"]])
+    for s in range(0, len(allf), 64):   # same call sequence as processor_uniprompt_stage2.py:246-261
+        feat = torch.from_numpy(allf[s:s + 64]).to(DEV)
+        ev.update((feat, tuple(int(x) for x in pids[s:s + 64]), tuple(int(x) for x in cams[s:s + 64])))
+    cmc, mAP, distmat, out_pids, out_cams, qf, gf = ev.compute()
+    out = capsys.readouterr().out
+    assert "The test feature is normalized" in out and "=> Computing DistMat with euclidean_distance" in out
+    assert cmc.dtype == np.float32 and cmc.shape == g["ref_cmc"].shape
+    assert np.abs(cmc - g["ref_cmc"]).max() <= 1e-6 and abs(mAP - g["ref_mAP"]) <= 1e-6
+    d = np.asarray(distmat)
+    qn, gn = norm_feats(g)
+    assert d.shape == g["dist_euclid"].shape and np.all(np.abs(d - g["dist_euclid"]) <= dist_tol(qn, gn))
+    assert len(out_pids) == len(allf) and qf.shape == g["qf"].shape and gf.shape == g["gf"].shape
+    # bit-exactness when ranking the reference's own matrix
+    cmc2, mAP2 = metrics.eval_func(g["dist_euclid"], g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
+    assert np.array_equal(cmc2, g["ref_stable_cmc"]) and mAP2 == g["ref_stable_mAP"]
+
+
+def test_evaluator_reranking_flag(golden_dir, capsys):
+    g = load(golden_dir, "rerank_small")
+    ev = metrics.R1_mAP_eval(len(g["qf"]), reranking=True)
+    ev.reset()
+    ev.update((torch.from_numpy(np.concatenate([g["qf"], g["gf"]])), np.concatenate([g["q_pid"], g["g_pid"]]),
+               np.concatenate([g["q_cam"], g["g_cam"]])))
+    cmc, mAP, *_ = ev.compute()
+    assert "=> Enter reranking" in capsys.readouterr().out
+    assert abs(mAP - g["rr_50_15_30_mAP"]) <= 1e-4     # utils/metrics.py:127 runs k1=50, k2=15, lambda=0.3
+
+
+# ------------------------------------------------------------------------------------ full shapes
+def _full(golden_dir):
+    p = os.path.join(golden_dir, "full_shapes.json")
+    if not os.path.exists(p):
+        pytest.skip("full-shape goldens missing")
+    return json.load(open(p))
+
+
+def _run_evaluator(shape, **kw):
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_shape(shape)
+    ev = metrics.R1_mAP_eval(qf.shape[0], **kw)
+    ev.reset()
+    ev.update((qf, q_pid, q_cam))
+    for s in range(0, gf.shape[0], 8192):
+        ev.update((gf[s:s + 8192], g_pid[s:s + 8192], g_cam[s:s + 8192]))
+    return ev.compute(), (q_pid, g_pid, q_cam, g_cam)
+
+
+def test_market_shape_matches_reference_scalars(golden_dir):
+    rec = _full(golden_dir)["c1"]
+    (cmc, mAP, distmat, *_), labels = _run_evaluator("market")
+    assert abs(mAP - rec["ref_mAP"]) <= 1e-6 and np.abs(cmc - np.array(rec["ref_cmc"], np.float32)).max() <= 1e-6
+    d = distmat.device_tensor
+    assert abs(float(d.double().sum()) - rec["dist_sum"]) <= 1e-6 * rec["dist_sum"]
+    # properties at full size: re-ranking the SAME device matrix through the public API is idempotent
+    cmc2, mAP2 = metrics.eval_func(distmat, *labels)
+    assert np.array_equal(cmc, cmc2) and mAP == mAP2
+    # junk mode and arccos metric against the reference with its junk rule switched on
+    cmcj, mAPj = metrics.eval_func(distmat, *labels, junk="pid_cam")
+    assert abs(mAPj - rec["ref_junk_mAP"]) <= 1e-6
+    (cmca, mAPa, *_), _ = _run_evaluator("market", metric="arccos")
+    assert abs(mAPa - rec["ref_arccos_mAP"]) <= 2e-5
+
+
+def test_market_shape_bf16_mode_stated_delta(golden_dir):
+    rec = _full(golden_dir)["c1"]
+    (cmc, mAP, *_), _ = _run_evaluator("market", precision="bf16")
+    assert abs(mAP - rec["ref_mAP"]) <= 2e-4 and abs(float(cmc[0]) - rec["ref_cmc"][0]) <= 2e-3
+
+
+def test_market_shape_reranking_matches_reference(golden_dir):
+    rec = _full(golden_dir)
+    if "c3" not in rec:
+        pytest.skip("c3 golden missing")
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_shape("market")
+    feats = torch.nn.functional.normalize(torch.cat([qf, gf]), dim=1, p=2)
+    fd = reranking.re_ranking(feats[: qf.shape[0]], feats[qf.shape[0]:], 20, 6, 0.3)
+    r = rec["c3"]["rr_20_6"]
+    assert abs(float(fd.min()) - r["final_min"]) <= 2e-3 and abs(float(fd.max()) - r["final_max"]) <= 2e-3
+    assert abs(float(fd.astype(np.float64).sum()) - r["final_sum"]) <= 1e-4 * r["final_sum"]
+    cmc, mAP = metrics.eval_func(fd, q_pid, g_pid, q_cam, g_cam)
+    assert abs(mAP - r["mAP"]) <= 1e-4 and abs(float(cmc[0]) - r["cmc"][0]) <= 1e-3
