@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — query x gallery pairs/s through distance + ranking + CMC/mAP on the MSMT17-shaped set
+(BASELINE.json: 11,659 x 82,161 x 1280-d), plus re-rank ms, on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload msmt17|market|cctv]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+A "step" is one pass of the hot path over one batch of synthetic features:
+  value : features already resident in HBM -> normalise + operand planes -> distance matrix ->
+          rank / CMC / AP kernels -> per-query results to the host -> (cmc, mAP)
+  e2e   : the same through the reference-facing API (R1_mAP_eval.reset/update/compute) fed from
+          PINNED HOST batches, host->device copies and the result read-back inside the timed region
+Multi-GPU: query rows are sharded (every rank evaluates its own MSMT17-sized query shard against the
+replicated gallery: weak scaling), per-query results are all-gathered once, rank 0 reduces.
+The reference arm (--impl reference) times the reference's CPU algorithm (oracle port: torch-CPU
+sgemm + numpy argsort + Python loop; the Python reference itself cannot travel to the GPU box) on a
+bounded sample with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mp_reid_b200 import synth  # noqa: E402
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_pass(qf, gf, q_pid, g_pid, q_cam, g_cam):
+    """One pass of the reference's CPU algorithm (oracle port) -> (cmc, mAP)."""
+    from oracle import mpreid_oracle as orc
+    feats = orc.l2_normalize(np.concatenate([qf, gf]))
+    d = orc.sq_euclidean(feats[: len(qf)], feats[len(qf):])
+    return orc.eval_func(d, q_pid, g_pid, q_cam, g_cam, sort_kind=None)  # numpy's default sort, as the reference calls it
+
+
+def cpu_sample(data, n_queries):
+    qf, gf, q_pid, g_pid, q_cam, g_cam = data
+    return qf[:n_queries].numpy(), gf.numpy(), q_pid[:n_queries], g_pid, q_cam[:n_queries], g_cam
+
+
+def run_reference(args, data, workload):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    G = data[1].shape[0]
+    nq = max(8, min(data[0].shape[0], int(args.ref_queries)))
+    sample = cpu_sample(data, nq)
+    import contextlib, io
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            cmc, mAP = cpu_reference_pass(*sample)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = nq * G * len(times) / total
+    line = {
+        "impl": "reference", "metric": "query x gallery pairs/sec (dist+rank+mAP)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "Q_sample": nq, "G": G, "D": int(data[0].shape[1]), "distance": "sqeuclid",
+                   "feat_norm": True, "junk": "none"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"first {nq} queries x full gallery per step (torch-CPU sgemm, numpy argsort, Python loop)"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "mAP_sample": float(mAP),
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, data, workload):
+    from mp_reid_b200 import engine as E
+    from mp_reid_b200 import metrics
+    from mp_reid_b200.reranking import _rerank_device
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    qf, gf, q_pid, g_pid, q_cam, g_cam = data
+    Q, G, D = qf.shape[0], gf.shape[0], qf.shape[1]
+    prec, junk, metric = args.precision, args.junk, args.metric
+
+    # ---- inputs resident in HBM (device-timed `value`) and in pinned host memory (`e2e`)
+    feats_dev = torch.cat([qf, gf]).to(dev)
+    lab = dict(q_pid=torch.from_numpy(q_pid).to(dev), g_pid=torch.from_numpy(g_pid).to(dev),
+               q_cam=torch.from_numpy(q_cam).to(dev), g_cam=torch.from_numpy(g_cam).to(dev))
+    batch = 8192
+    host_batches = []
+    allf = torch.cat([qf, gf])
+    pids_all = np.concatenate([q_pid, g_pid])
+    cams_all = np.concatenate([q_cam, g_cam])
+    for s in range(0, allf.shape[0], batch):
+        host_batches.append((allf[s:s + batch].clone().pin_memory(), pids_all[s:s + batch], cams_all[s:s + batch]))
+    del allf
+    dist_buf = E.alloc_dist(Q, G, dev)
+    launches = [0]
+
+    def gather_and_reduce(first_hit, ap, num_rel):
+        packed = torch.stack([first_hit.double(), ap, num_rel.double()])  # [3, Q]; counts are exact in fp64
+        if distributed:
+            out = torch.empty((world, 3, Q), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, packed.contiguous())
+            if rank != 0:
+                return None
+            h = out.cpu().numpy()
+            fh = h[:, 0].reshape(-1).astype(np.int32); apv = h[:, 1].reshape(-1); nr = h[:, 2].reshape(-1).astype(np.int32)
+        else:
+            h = packed.cpu().numpy()
+            fh, apv, nr = h[0].astype(np.int32), h[1], h[2].astype(np.int32)
+        return E.reduce_cmc_map(fh, apv, nr, 50, G)
+
+    def step_resident():
+        prep = E.prep_rows(feats_dev, normalize=True, precision=prec, keep_xn=False)
+        q, g = prep.rows(0, Q), prep.rows(Q, Q + G)
+        d = E.dist_matrix(q, g, metric, prec, out=dist_buf)
+        fh, ap, nr = E.rank_eval(d, lab["q_pid"], lab["g_pid"], lab["q_cam"], lab["g_cam"], junk)
+        launches[0] += 1 + 1 + 8
+        return gather_and_reduce(fh, ap, nr)
+
+    import contextlib, io
+
+    def step_e2e():
+        ev = metrics.R1_mAP_eval(Q, max_rank=50, feat_norm=True, precision=prec, junk=junk, metric=metric)
+        ev.reset()
+        for f, p, c in host_batches:
+            ev.update((f, p, c))
+        with contextlib.redirect_stdout(io.StringIO()):
+            cmc, mAP, *_ = ev.compute()
+        return cmc, mAP
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        res = None
+        for _ in range(warmup):
+            res = fn()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if distributed:
+            dist.barrier()
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, clocks
+
+    launches[0] = 0
+    ms_total, res, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    n_launch = launches[0] - 10 * args.warmup
+    ms_step = ms_total / args.steps
+    value = world * Q * G / (ms_step * 1e-3)
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e_total, res_e2e, _ = timed(step_e2e, e2e_steps, 1)
+    ms_e2e = ms_e2e_total / e2e_steps
+    e2e_value = world * Q * G / (ms_e2e * 1e-3)
+
+    # ---- per-kernel timing of the dominant kernel (distance GEMM) and the HBM-bound rank kernels
+    def kernel_ms(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    prep = E.prep_rows(feats_dev, normalize=True, precision=prec, keep_xn=False)
+    q, g = prep.rows(0, Q), prep.rows(Q, Q + G)
+    gemm_ms = kernel_ms(lambda: E.dist_matrix(q, g, metric, prec, out=dist_buf), max(3, args.steps))
+    rank_ms = kernel_ms(lambda: E.rank_eval(dist_buf, lab["q_pid"], lab["g_pid"], lab["q_cam"], lab["g_cam"], junk), max(3, args.steps))
+    prep_ms = kernel_ms(lambda: E.prep_rows(feats_dev, normalize=True, precision=prec, keep_xn=False), max(3, args.steps))
+    pk = peaks()
+    flops = 2.0 * Q * G * D
+    achieved_tf = flops / (gemm_ms * 1e-3) / 1e12
+    if prec == "bf16":
+        peak_tf, peak_note = pk["bf16"], f"{pk['source']} cuBLAS bf16 burst"
+    else:
+        # fp32-accurate mode issues 3 TF32 MMAs per product: denominator = dense TF32 peak / 3, TF32 peak measured here
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+        t_tf32 = min(kernel_ms(lambda: torch.matmul(a, b), 5) for _ in range(3))
+        tf32_peak = 2 * 8192 ** 3 / (t_tf32 * 1e-3) / 1e12
+        del a, b
+        peak_tf, peak_note = tf32_peak / 3.0, f"cuBLAS TF32 8192^3 measured in this run ({tf32_peak:.0f} TFLOP/s) / 3 MMAs per product"
+    roofline = {"bound": "tensor", "kernel": "k_dist_tc", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_note,
+                "algorithmic": "2*Q*G*D flops per launch", "ms_per_launch": gemm_ms}
+    rank_gbs = (4.0 * Q * G) / (rank_ms * 1e-3) / 1e9
+    stages = {"prep_ms": prep_ms, "dist_ms": gemm_ms, "rank_eval_ms": rank_ms,
+              "rank_eval_roofline": {"bound": "hbm", "achieved": rank_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                     "frac": rank_gbs / pk["hbm"], "algorithmic": "4*Q*G bytes (distance matrix read once)",
+                                     "peak_source": pk["source"]}}
+
+    # ---- re-rank ms (second half of the headline metric) on a shape that is cheap enough to repeat
+    rerank = None
+    if args.rerank != "none":
+        rq, rg = (Q, G) if args.rerank == "full" else (min(Q, 3368), min(G, 15913))
+        sub = torch.cat([feats_dev[:rq], feats_dev[Q:Q + rg]])
+        def rr():
+            p = E.prep_rows(sub, normalize=True, precision=prec, keep_xn=False)
+            dfin = _rerank_device(p, rq, args.k1, args.k2, 0.3, prec)
+            return E.rank_eval(dfin, lab["q_pid"][:rq], lab["g_pid"][:rg], lab["q_cam"][:rq], lab["g_cam"][:rg], junk)
+        rr_ms = kernel_ms(rr, 2)
+        fh, ap, nr = rr()
+        _, rr_map = E.reduce_cmc_map(fh.cpu().numpy(), ap.cpu().numpy(), nr.cpu().numpy(), 50, rg)
+        rerank = {"ms": rr_ms, "Q": rq, "G": rg, "k1": args.k1, "k2": args.k2, "lambda": 0.3, "mAP": float(rr_map),
+                  "includes": "prep + (Q+G)^2 distance + re-ranking + rank/AP kernels"}
+
+    if rank == 0:
+        # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and args.cpu_queries > 0:
+            torch.set_num_threads(os.cpu_count())
+            nq = min(Q, args.cpu_queries)
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                _, cpu_map = cpu_reference_pass(*cpu_sample(data, nq))
+            dt = time.perf_counter() - t0
+            cpu = {"value": nq * G / dt, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"first {nq} of {Q} queries x full gallery, one pass, {dt:.1f} s "
+                             "(torch-CPU sgemm + numpy argsort + Python loop, oracle port of utils/metrics.py)"}
+        cmc, mAP = res
+        line = {
+            "metric": "query x gallery pairs/sec (dist+rank+mAP)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core split)" if prec != "bf16" else "bf16", "data": "synthetic",
+            "config": {"workload": workload, "Q_per_gpu": Q, "G": G, "D": D, "distance": metric, "precision": prec, "feat_norm": True,
+                       "junk": junk, "l2": "inputs larger than L2 (features 0.48 GB, distance matrix 3.8 GB per pass)",
+                       "sharding": "query rows per GPU, gallery replicated, one all-gather of per-query results"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int((Q + G) * D * 4 + (Q + G) * 16), "d2h_bytes_per_step": int(Q * 24),
+                    "api": "R1_mAP_eval.reset/update/compute from pinned host batches"},
+            "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+            "rerank": rerank, "mAP": float(mAP), "rank1": float(cmc[0]),
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="msmt17", choices=["msmt17", "market", "cctv"])
+    ap.add_argument("--precision", default=os.environ.get("MPREID_PRECISION", "3xtf32"))
+    ap.add_argument("--metric", default="sqeuclid")
+    ap.add_argument("--junk", default="none")
+    ap.add_argument("--rerank", default="market", choices=["none", "market", "full"])
+    ap.add_argument("--k1", type=int, default=20)
+    ap.add_argument("--k2", type=int, default=6)
+    ap.add_argument("--cpu-queries", type=int, default=1500, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--ref-queries", type=int, default=600, help="queries per step of the reference arm")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    s = synth.SHAPES[args.workload]
+    workload = f"{s.name} shape {int(round(s.Q * args.scale))} x {int(round(s.G * args.scale))} x {s.D}, euclidean, dist+rank+CMC/mAP"
+    world = env_int("WORLD_SIZE", 1)
+    if args.impl == "reference" and env_int("RANK", 0) != 0:
+        return
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    data = synth.make_shape(args.workload, args.scale)
+    if args.impl == "reference":
+        run_reference(args, data, workload)
+    else:
+        run_ours(args, data, workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -452,7 +452,7 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, int N, int Q, float lambda
         const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
         const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
         const float dn = drow[t0 + c] / rmax;                                    // original_dist[i, Q+g]   (:46,72)
-        orow[t0 + c] = __half2float(jl) + dn * lambda_value;                     // (:95)
+        orow[t0 + c] = __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value)); // (:95) two roundings, no FMA contraction
       }
       __syncthreads();
     }
