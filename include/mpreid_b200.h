@@ -52,7 +52,9 @@ enum mpreid_metric {
 enum mpreid_precision {
   MPREID_FP32_SIMT = 0, /* plain fp32 FFMA tiles (validation / tiny shapes)                        */
   MPREID_3XTF32 = 1,    /* tcgen05 kind::tf32, error-compensated hi/lo split: fp32-accurate        */
-  MPREID_BF16 = 2       /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate             */
+  MPREID_BF16 = 2,      /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate             */
+  MPREID_3XFP16 = 3     /* tcgen05 kind::f16 on a per-row power-of-two scaled fp16 hi/lo split:
+                           fp32-accurate like 3xTF32 at twice the MMA rate                          */
 };
 
 enum mpreid_junk {
@@ -76,10 +78,14 @@ MPREID_API int mpreid_device_info(int device, int* sm_count, int* cc_major, int*
  *   hi, lo  [rows, Dp]  fp32 holding TF32-representable values, xn = hi + lo (+2^-22 rel.), zero
  *                       padded from D to Dp                                (both or neither)
  *   bf      [rows, Dp]  bf16 (round-to-nearest-even) copy of xn, zero padded (may be NULL)
- * Dp must be a multiple of 32 (TMA boxes are 128 B wide).  x may be fp32 only.            */
+ *   h_hi, h_lo [rows, Dp] fp16 split of the row scaled by 2^s (s per row such that max|xn|*2^s is in
+ *                       [512, 1024)):  xn * 2^s = h_hi + h_lo (+2^-22 rel.);  h_scale_inv[rows] = 2^-s
+ *                       (all three or none)
+ * Dp must be a multiple of 32 (fp32 planes) / 64 (16-bit planes): TMA boxes are 128 B wide.  x is fp32. */
 MPREID_API int mpreid_prep_rows(const float* x, int64_t rows, int64_t D, int64_t ld_x, int normalize,
                      float* xn, int64_t ld_xn, float* sqnorm, float* norm,
-                     float* hi, float* lo, uint16_t* bf, int64_t Dp, void* stream);
+                     float* hi, float* lo, uint16_t* bf,
+                     uint16_t* h_hi, uint16_t* h_lo, float* h_scale_inv, int64_t Dp, void* stream);
 
 /* ---- distance matrix --------------------------------------------------------------------------
  * Replaces euclidean_distance (utils/metrics.py:7-13), cosine_similarity (utils/metrics.py:15-25),
@@ -88,12 +94,14 @@ MPREID_API int mpreid_prep_rows(const float* x, int64_t rows, int64_t D, int64_t
  *   precision MPREID_FP32_SIMT : qa/ga = fp32 features [*, ldk]; qb/gb ignored
  *   precision MPREID_3XTF32    : qa/ga = hi planes, qb/gb = lo planes, [*, ldk] fp32, ldk % 32 == 0
  *   precision MPREID_BF16      : qa/ga = bf16 planes [*, ldk], ldk % 64 == 0;    qb/gb ignored
+ *   precision MPREID_3XFP16    : qa/ga = fp16 hi planes, qb/gb = fp16 lo planes, [*, ldk], ldk % 64 == 0,
+ *                                q_scale/g_scale = the per-row 2^-s of mpreid_prep_rows (NULL otherwise)
  *   q_aux/g_aux: squared norms for the euclidean metrics, norms for MPREID_ARCCOS, unused (may be
  *   NULL) for MPREID_ONE_MINUS_DOT.
  *   row_max (optional, [Q], must be pre-filled with -inf): per-row maximum of the written values
  *   (the column max of utils/reranking.py:46, by symmetry).                                    */
 MPREID_API int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga, const void* gb,
-                       const float* q_aux, const float* g_aux,
+                       const float* q_aux, const float* g_aux, const float* q_scale, const float* g_scale,
                        int64_t Q, int64_t G, int64_t K, int64_t ldk,
                        int metric, int precision,
                        float* out, int64_t ld_out, float* row_max, void* stream);

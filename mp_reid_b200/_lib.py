@@ -16,12 +16,12 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "mpreid_b200.h")
 
 # enums of include/mpreid_b200.h
 SQEUCLID, ARCCOS, ONE_MINUS_DOT, SQRT_EUCLID = 0, 1, 2, 3
-FP32_SIMT, X3TF32, BF16 = 0, 1, 2
+FP32_SIMT, X3TF32, BF16, X3FP16 = 0, 1, 2, 3
 JUNK_NONE, JUNK_PID_CAM = 0, 1
 
 METRICS = {"sqeuclid": SQEUCLID, "euclidean": SQEUCLID, "arccos": ARCCOS, "cosine": ARCCOS,
            "one_minus_dot": ONE_MINUS_DOT, "1-cos": ONE_MINUS_DOT, "sqrt_euclid": SQRT_EUCLID}
-PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "fp32": X3TF32, "3xtf32": X3TF32, "bf16": BF16}
+PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "3xtf32": X3TF32, "bf16": BF16, "3xfp16": X3FP16, "fp32": X3FP16}
 JUNKS = {"none": JUNK_NONE, "pid_cam": JUNK_PID_CAM}
 
 _p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
@@ -30,8 +30,8 @@ SIGNATURES = {
     "mpreid_last_error": (C.c_char_p, []),
     "mpreid_abi_version": (_i32, []),
     "mpreid_device_info": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
-    "mpreid_prep_rows": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
-    "mpreid_dist_matrix": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
+    "mpreid_prep_rows": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "mpreid_dist_matrix": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
     "mpreid_rank_eval_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mpreid_rank_eval": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _sz, _i64, _p, _p]),
     "mpreid_row_topk": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),

@@ -30,7 +30,7 @@ int sm_count_of_current_device() {
 int launch_dist_simt(const float* q, const float* g, const float* q_aux, const float* g_aux, int64_t Q, int64_t G,
                      int64_t K, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st);
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
-                   int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
+                   const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
                    float* row_max, cudaStream_t st);
 
 }  // namespace mpreid
@@ -51,7 +51,7 @@ extern "C" int mpreid_device_info(int device, int* sm_count, int* cc_major, int*
 }
 
 extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga, const void* gb,
-                                  const float* q_aux, const float* g_aux,
+                                  const float* q_aux, const float* g_aux, const float* q_scale, const float* g_scale,
                                   int64_t Q, int64_t G, int64_t K, int64_t ldk,
                                   int metric, int precision,
                                   float* out, int64_t ld_out, float* row_max, void* stream) {
@@ -64,9 +64,11 @@ extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MPREID_FP32_SIMT)
     return launch_dist_simt((const float*)qa, (const float*)ga, q_aux, g_aux, Q, G, K, ldk, metric, out, ld_out, row_max, st);
-  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16, "dist_matrix: unknown precision %d", precision);
-  MPREID_REQUIRE(precision != MPREID_3XTF32 || (qb && gb), "dist_matrix: 3xTF32 needs the lo planes");
-  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, precision, out, ld_out, row_max, st);
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16,
+                 "dist_matrix: unknown precision %d", precision);
+  MPREID_REQUIRE(precision == MPREID_BF16 || (qb && gb), "dist_matrix: the split modes need the lo planes");
+  MPREID_REQUIRE(precision != MPREID_3XFP16 || (q_scale && g_scale), "dist_matrix: 3xFP16 needs the per-row scales");
+  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, st);
 }
 
 extern "C" double mpreid_host_average_precision(const int32_t* ranks_host, int m, int64_t n) {

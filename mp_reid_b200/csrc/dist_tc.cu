@@ -41,6 +41,9 @@ template <> struct Cfg<MPREID_3XTF32> {
 template <> struct Cfg<MPREID_BF16> {
   static constexpr int PLANES = 1, ELEM = 2, UMMA_K = 16, STAGES = 4, FMT = 1 /*BF16*/;
 };
+template <> struct Cfg<MPREID_3XFP16> {
+  static constexpr int PLANES = 2, ELEM = 2, UMMA_K = 16, STAGES = 2, FMT = 0 /*F16*/;
+};
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,8 +118,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // K-major operand, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
 // bits: [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -150,10 +169,11 @@ struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int PREC, bool VEC>
+template <int PREC, int METRIC, bool VEC>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
-          int Q, int G, int num_k_blocks, int metric, float* __restrict__ out, int64_t ld_out,
+          const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
+          float* __restrict__ out, int64_t ld_out,
           float* __restrict__ row_max, int m_blocks, int n_blocks) {
   using C = Cfg<PREC>;
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
@@ -170,6 +190,8 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  const uint32_t gvec_base = bar_base + 256u;              // 2 x 256 float2: per-column (aux, scale) of the tile
+  const uint32_t stage_base = gvec_base + 2u * BN * 8u;    // 4 warps x 4 KB output staging
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -253,44 +275,87 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     }
   } else {
     // ================================ epilogue ================================
+    // Per tile: (1) the 4 epilogue warps stage the tile's 256 gallery terms (norm, 2^-s scale) in
+    // shared memory once; (2) TMEM is read 32 columns at a time with the NEXT chunk's tcgen05.ld in
+    // flight while the current one is finished; (3) results go through a per-warp 32x32 swizzled
+    // staging tile so that every global store instruction writes four full 128-byte lines.
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
+    float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 1024;
+    float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const int gm = t.m_blk * BM + row;
+      const int gm0 = t.m_blk * BM + quad * 32;
+      const int gm = gm0 + lane;
       const bool row_ok = gm < Q;
       const float qa = (row_ok && q_aux) ? q_aux[gm] : 0.f;
-      float* orow = out + (int64_t)gm * ld_out;
+      const float qs = (PREC == MPREID_3XFP16 && row_ok) ? q_scale[gm] : 1.f;
       float rmax = -INFINITY;
+      float2* gvec = gvec_all + as * BN;
+#pragma unroll
+      for (int c = et; c < BN; c += 128) {
+        const int gn = t.n_blk * BN + c;
+        float2 v = make_float2(1.f, 1.f);
+        if (gn < G) {
+          if (g_aux) v.x = __ldg(g_aux + gn);
+          if (PREC == MPREID_3XFP16) v.y = __ldg(g_scale + gn);
+        }
+        gvec[c] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // gvec visible to the 4 epilogue warps
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr0 + (uint32_t)c0, r);
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        // 64 accumulator columns per TMEM load; the wait follows the load directly (an asynchronous
+        // tcgen05.ld must not stay in flight across compiler-scheduled code: its destination
+        // registers may have been re-assigned by then)
+        uint32_t acc[64];
+        tmem_ld64(taddr0 + (uint32_t)c0, acc);
         tmem_ld_wait();
-        const int gn0 = t.n_blk * BN + c0;
-        if (row_ok && gn0 < G) {
-          float d[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gn = gn0 + j;
-            const float ga = (g_aux && gn < G) ? __ldg(g_aux + gn) : 1.f;
-            d[j] = finish_distance_rt(metric, __uint_as_float(r[j]), qa, ga);
-            if (gn < G) rmax = fmaxf(rmax, d[j]);
-          }
-          if (VEC && gn0 + 32 <= G) {
+        for (int half = 0; half < 2; ++half) {
+          const int cc = c0 + half * 32;
+          const int gn0 = t.n_blk * BN + cc;
+          if (gm0 < Q && gn0 < G) {   // warp-uniform
+            float d[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(orow + gn0 + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
-          } else {
+            for (int j = 0; j < 32; ++j) {
+              const float2 gv = gvec[cc + j];                       // broadcast read
+              float dot = __uint_as_float(acc[half * 32 + j]);
+              if (PREC == MPREID_3XFP16) dot = dot * qs * gv.y;     // undo the 2^s row scales (exact)
+              d[j] = finish_distance<METRIC>(dot, qa, gv.x);
+              if (gn0 + j < G) rmax = fmaxf(rmax, d[j]);
+            }
+            // stage: lane == row, 16-byte chunk c of the row goes to position c ^ (row & 7)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (gn0 + j < G) orow[gn0 + j] = d[j];
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                  make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
+            __syncwarp();
+            // drain: 8 lanes cover one 128-byte row, 4 rows per instruction
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3), c = lane & 7;
+              const float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((c ^ (r & 7)) << 2));
+              const int grow = gm0 + r, gcol = gn0 + 4 * c;
+              if (grow < Q) {
+                float* dst = out + (int64_t)grow * ld_out + gcol;
+                if (VEC && gcol + 4 <= G) {
+                  *reinterpret_cast<float4*>(dst) = v;
+                } else {
+                  if (gcol < G) dst[0] = v.x;
+                  if (gcol + 1 < G) dst[1] = v.y;
+                  if (gcol + 2 < G) dst[2] = v.z;
+                  if (gcol + 3 < G) dst[3] = v.w;
+                }
+              }
+            }
+            __syncwarp();
           }
         }
       }
@@ -329,7 +394,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, 
   cuuint64_t strides[1] = {(cuuint64_t)ldk * elem};
   cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MPREID_ERR_CUDA; }
@@ -338,7 +403,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, 
 
 template <int PREC>
 static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
-                  int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st) {
+                  const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st) {
   using C = Cfg<PREC>;
   constexpr int kpb = ROW_BYTES / C::ELEM;
   MPREID_REQUIRE(ldk % kpb == 0, "dist_tc: operand planes must be padded to a multiple of %d elements (got %lld)", kpb, (long long)ldk);
@@ -358,11 +423,20 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   const int sms = sm_count_of_current_device();
   const int grid = (int)(total < sms ? total : sms);
   constexpr int STAGE_BYTES = C::PLANES * (BM + BN) * ROW_BYTES;
-  const int smem = C::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const int smem = C::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
   const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  auto kern = vec ? k_dist_tc<PREC, true> : k_dist_tc<PREC, false>;
+  using KernT = decltype(&k_dist_tc<PREC, MPREID_SQEUCLID, true>);   // no casts: a signature mismatch must not compile
+  KernT kern = nullptr;
+#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, M, true> : &k_dist_tc<PREC, M, false>
+  switch (metric) {
+    case MPREID_SQEUCLID: MPREID_PICK(MPREID_SQEUCLID); break;
+    case MPREID_ARCCOS: MPREID_PICK(MPREID_ARCCOS); break;
+    case MPREID_ONE_MINUS_DOT: MPREID_PICK(MPREID_ONE_MINUS_DOT); break;
+    default: MPREID_PICK(MPREID_SQRT_EUCLID); break;
+  }
+#undef MPREID_PICK
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, (int)Q, (int)G, (int)(ldk / kpb), metric, out, ld_out, row_max,
+  kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, (int)Q, (int)G, (int)(ldk / kpb), out, ld_out, row_max,
                                     m_blocks, n_blocks);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
@@ -371,7 +445,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
 }  // namespace tc
 
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
-                   int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
+                   const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
                    float* row_max, cudaStream_t st) {
   int dev = 0, major = 0;
   MPREID_CUDA_CHECK(cudaGetDevice(&dev));
@@ -381,8 +455,10 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
     return MPREID_ERR_UNSUPPORTED;
   }
   if (precision == MPREID_3XTF32)
-    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, out, ld_out, row_max, st);
-  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, Q, G, ldk, metric, out, ld_out, row_max, st);
+    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
+  if (precision == MPREID_3XFP16)
+    return tc::launch<MPREID_3XFP16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
+  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
 }
 
 }  // namespace mpreid

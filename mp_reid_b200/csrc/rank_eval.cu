@@ -16,7 +16,7 @@ namespace mpreid {
 
 static constexpr int64_t kEmptyKey = INT64_MIN;
 static constexpr int kRankThreads = 256;
-static constexpr int kRankCap = 2048;  // same-pid keys sorted per pass in shared memory
+static constexpr int kRankCap = 1024;  // same-pid keys sorted per pass in shared memory
 
 struct RankWs {
   int64_t* keys;    // [T]
@@ -210,23 +210,120 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
 }
 
 // ------------------------------------------------------------------------------- rank_count
+// Row streaming is split in two so that the expensive part never runs divergently:
+//   classify  every lane tests its 16 elements against the farthest same-pid distance with ONE float
+//             compare each (branch free) and appends the few survivors to its warp's queue;
+//   drain     when a warp's queue holds >= 128 entries the warp processes them densely, one entry per
+//             lane: 256-bin lookup table -> short binary search among the sorted keys -> histogram
+//             bump, aggregated across the lanes that hit the same bucket (match.any) so the popular
+//             last bucket costs one shared-memory atomic per warp, not 32 serialised ones.
+// (With ~7 % survivors a per-element branch would be taken by ~90 % of the warps.)
+static constexpr int kWarps = kRankThreads / 32;
+static constexpr int kQueueDrain = 128;                 // drain threshold
+static constexpr int kQueueCap = kQueueDrain + 32 * 16; // + one full warp chunk
+
 struct RankSmem {
   uint64_t keys[kRankCap];
   uint32_t hist[kRankCap + 1];
   uint32_t scratch[kRankThreads];
+  uint16_t lut[257];
+  uint2 queue[kWarps][kQueueCap];   // (float bits, gallery index)
   int32_t misc[4];
 };
 
-__device__ __forceinline__ void count_one(float v, uint32_t j, uint32_t tmax, const uint64_t* keys, int m, uint32_t* hist) {
-  const uint32_t o = order_key(v);
-  if (o > tmax) return;  // beyond the farthest same-pid entry: the common case
-  const uint64_t key = ((uint64_t)o << 32) | j;
-  int lo = 0, hi = m;    // b = #keys < key
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (keys[mid] < key) lo = mid + 1; else hi = mid;
+struct RowCtx {
+  const uint64_t* keys; const uint16_t* lut; uint32_t* hist;
+  int m; uint32_t omin, tmax; int shift; float tmax_f;
+};
+
+__device__ __forceinline__ void drain_queue(const RowCtx& c, uint2* q, int count, int lane) {
+  for (int e0 = 0; e0 < count; e0 += 32) {   // warp-uniform trip count: every lane reaches match.any
+    const int e = e0 + lane;
+    int b = -1;
+    if (e < count) {
+      const uint2 it = q[e];
+      const uint32_t o = order_key(__uint_as_float(it.x));
+      if (o <= c.tmax) {   // re-check in key space (the float pre-test lets -0.0 / NaN through)
+        const uint64_t key = ((uint64_t)o << 32) | it.y;
+        int lo = 0, hi = 0;
+        if (o >= c.omin) { const uint32_t bin = (o - c.omin) >> c.shift; lo = c.lut[bin]; hi = c.lut[bin + 1]; }
+        // keys before lo sit in earlier bins (< key), keys from hi on in later bins (> key): #keys < key is in [lo, hi]
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (c.keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        b = lo;
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&c.hist[b], (uint32_t)__popc(peers));
   }
-  atomicAdd(&hist[lo], 1u);
+}
+
+__device__ __forceinline__ void stream_row(const float* __restrict__ row, int G, const RowCtx& c, uint2* q) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  int qcount = 0;  // warp-uniform
+  int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
+  head = min(head, G);
+  const int nvec = (G - head) >> 2;
+  const float4* rv = reinterpret_cast<const float4*>(row + head);
+  constexpr int U = 4;
+  const float tmax_f = c.tmax_f;
+  // ragged ends (< 4 elements each) go through the same queue, handled by warp 0
+  if (tid < 32) {
+    uint32_t mask = 0; float v[2] = {0.f, 0.f}; uint32_t jj[2] = {0u, 0u};
+    if (lane < head) { v[0] = row[lane]; jj[0] = lane; mask |= !(v[0] > tmax_f) ? 1u : 0u; }
+    const int t = head + 4 * nvec + lane;
+    if (t < G) { v[1] = row[t]; jj[1] = t; mask |= !(v[1] > tmax_f) ? 2u : 0u; }
+    const int n = __popc(mask);
+    int incl = n;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    int pos = qcount + incl - n;
+    if (mask & 1u) q[pos++] = make_uint2(__float_as_uint(v[0]), jj[0]);
+    if (mask & 2u) q[pos++] = make_uint2(__float_as_uint(v[1]), jj[1]);
+    qcount += __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+  }
+  for (int v0 = 0; v0 < nvec; v0 += kRankThreads * U) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * kRankThreads + tid;
+      x[u] = v < nvec ? ldg_stream4(rv + v) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mask |= (!(x[u].x > tmax_f) ? 1u : 0u) << (4 * u);
+      mask |= (!(x[u].y > tmax_f) ? 2u : 0u) << (4 * u);
+      mask |= (!(x[u].z > tmax_f) ? 4u : 0u) << (4 * u);
+      mask |= (!(x[u].w > tmax_f) ? 8u : 0u) << (4 * u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)   // padding lanes loaded +inf; +inf <= +inf only if tmax_f is +inf: mask them out
+      if (v0 + u * kRankThreads + tid >= nvec) mask &= ~(0xfu << (4 * u));
+    const int n = __popc(mask);
+    int incl = n;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      int pos = qcount + incl - n;
+      if (mask) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t j = head + 4 * (v0 + u * kRankThreads + tid);
+          if (mask & (1u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].x), j);
+          if (mask & (2u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].y), j + 1);
+          if (mask & (4u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].z), j + 2);
+          if (mask & (8u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].w), j + 3);
+        }
+      }
+      qcount += total;
+      __syncwarp();
+      if (qcount >= kQueueDrain) { drain_queue(c, q, qcount, lane); qcount = 0; __syncwarp(); }
+    }
+  }
+  if (qcount) drain_queue(c, q, qcount, lane);
 }
 
 __global__ void __launch_bounds__(kRankThreads)
@@ -235,7 +332,8 @@ k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
              const int32_t* __restrict__ list, const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_cnt,
              const int32_t* __restrict__ q_off, const int32_t* __restrict__ status,
              int32_t* pos_tmp, int32_t* pos_rank, int32_t* first_hit, int32_t* num_rel, int32_t* row_len) {
-  __shared__ RankSmem s;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RankSmem& s = *reinterpret_cast<RankSmem*>(smem_raw);
   if (status[0] != 0) return;  // workspace overflow: the host re-runs with a larger capacity
   const int tid = threadIdx.x;
   for (int q = blockIdx.x; q < Q; q += gridDim.x) {
@@ -259,35 +357,27 @@ k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
       for (int i = tid; i <= m; i += kRankThreads) s.hist[i] = 0;
       __syncthreads();
       bitonic_sort_u64<kRankThreads>(s.keys, P);
-      const uint32_t tmax = (uint32_t)(s.keys[m - 1] >> 32);
-
-      // ---- one streaming pass over the row
-      int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
-      head = min(head, G);
-      if (tid < head) count_one(row[tid], tid, tmax, s.keys, m, s.hist);
-      const int nvec = (G - head) >> 2;
-      const float4* rv = reinterpret_cast<const float4*>(row + head);
-      constexpr int U = 4;
-      for (int v0 = tid; v0 < nvec; v0 += kRankThreads * U) {
-        float4 x[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int v = v0 + u * kRankThreads;
-          if (v < nvec) x[u] = ldg_stream4(rv + v);
+      RowCtx c;
+      c.keys = s.keys; c.lut = s.lut; c.hist = s.hist; c.m = m;
+      c.tmax = (uint32_t)(s.keys[m - 1] >> 32);
+      c.omin = (uint32_t)(s.keys[0] >> 32);
+      const uint32_t range = c.tmax - c.omin;
+      c.shift = range < 256u ? 0 : (32 - __clz(range)) - 8;
+      // float twin of tmax for the branch-free pre-test; NaN keys (0xffffffff) mean "everything may precede"
+      c.tmax_f = c.tmax == 0xffffffffu ? INFINITY : order_key_inv(c.tmax);
+      {
+        // lut[b] = #keys whose 32-bit order key is below the first value of bin b; lut[256] = m
+        const uint64_t lower = (uint64_t)c.omin + ((uint64_t)tid << c.shift);
+        int lo = 0, hi = m;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((uint64_t)(s.keys[mid] >> 32) < lower) lo = mid + 1; else hi = mid;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int v = v0 + u * kRankThreads;
-          if (v < nvec) {
-            const uint32_t j = head + 4 * v;
-            count_one(x[u].x, j, tmax, s.keys, m, s.hist);
-            count_one(x[u].y, j + 1, tmax, s.keys, m, s.hist);
-            count_one(x[u].z, j + 2, tmax, s.keys, m, s.hist);
-            count_one(x[u].w, j + 3, tmax, s.keys, m, s.hist);
-          }
-        }
+        s.lut[tid] = (uint16_t)lo;
+        if (tid == 0) s.lut[256] = (uint16_t)m;
       }
-      for (int j = head + 4 * nvec + tid; j < G; j += kRankThreads) count_one(row[j], j, tmax, s.keys, m, s.hist);
+      __syncthreads();
+      stream_row(row, G, c, s.queue[tid >> 5]);
       __syncthreads();
 
       // ---- rank of sorted key i = #row entries <= key i
@@ -391,7 +481,13 @@ extern "C" int mpreid_rank_eval(const float* dist, int64_t ld_dist, int64_t Q, i
   int sms = sm_count_of_current_device();
   int ctas_per_sm = 4;
   int grid = (int)((Q < (int64_t)sms * ctas_per_sm) ? Q : (int64_t)sms * ctas_per_sm);
-  k_rank_count<<<grid, kRankThreads, 0, st>>>(dist, ld_dist, (int)Q, (int)G, q_cam, g_cam, junk_mode != MPREID_JUNK_NONE,
+  const int rank_smem = (int)sizeof(RankSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_rank_count, cudaFuncAttributeMaxDynamicSharedMemorySize, rank_smem));
+    attr_set = true;
+  }
+  k_rank_count<<<grid, kRankThreads, rank_smem, st>>>(dist, ld_dist, (int)Q, (int)G, q_cam, g_cam, junk_mode != MPREID_JUNK_NONE,
                                               w.list, w.q_start, w.q_cnt, w.q_off, status, w.pos_tmp, w.pos_rank,
                                               first_hit, num_rel, w.row_len);
   k_ap_finalize<<<(unsigned)ceil_div(Q, 128), 128, 0, st>>>(w.pos_rank, w.q_off, num_rel, w.row_len, status, ap, (int)Q);

@@ -15,15 +15,18 @@
 namespace mpreid {
 
 static constexpr int kTopkThreads = 256;
-static constexpr int kTopkCap = 8192;       // candidate buffer entries (64 KB)
+static constexpr int kTopkCap = 6144;       // candidate buffer entries (48 KB)
 static constexpr int kTopkChunkVec = 4;     // float4 loads per thread per chunk
 static constexpr int kTopkMaxK = 2048;
 
 struct TopkSmem {
   uint64_t buf[kTopkCap];
-  int cnt;
+  uint64_t keep[kTopkMaxK];   // survivors of a cut, staged before they move to the buffer front
+  uint32_t hist[256];
+  int cnt, keep_cnt, sel_rank, sel_bin;
   float bound;       // raw-domain rejection bound
   uint64_t thr;      // current k-th best key (divided domain); ~0 = none yet
+  uint64_t sel_prefix;
 };
 
 __device__ __forceinline__ float4 ldg_stream4_topk(const float4* p) {
@@ -76,21 +79,62 @@ __device__ __forceinline__ void offer(TopkSmem& s, float bound, uint64_t thr, fl
   }
 }
 
-__device__ void compact(TopkSmem& s, int k, float r, bool has_scale) {
-  // sort what is there, keep the k smallest, tighten threshold and raw bound
+// Cut the candidate buffer back to its k smallest keys WITHOUT sorting it: MSB-first radix select
+// (8 bits per pass, shared-memory histogram) finds the k-th smallest 64-bit key, then one sweep
+// keeps the keys <= it (keys are unique, so exactly k survive).  All threads call; cnt >= k >= 1.
+__device__ void cut_to_k(TopkSmem& s, int k, float r, bool has_scale) {
+  const int tid = threadIdx.x;
   __syncthreads();
   const int cnt = s.cnt;
-  const int P = (int)next_pow2_u32((uint32_t)max(cnt, 1));
-  for (int i = cnt + threadIdx.x; i < P; i += kTopkThreads) s.buf[i] = ~0ull;
-  __syncthreads();
-  bitonic_sort_smem(s.buf, P);
-  if (threadIdx.x == 0) {
-    if (cnt >= k) {
-      s.cnt = k;
-      s.thr = s.buf[k - 1];
-      const uint32_t hi = (uint32_t)(s.thr >> 32);
-      s.bound = hi == 0xffffffffu ? INFINITY : raw_bound(order_key_inv(hi), r, has_scale);
+  if (tid == 0) { s.sel_prefix = 0; s.sel_rank = k; s.keep_cnt = 0; }
+  uint64_t mask = 0;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    s.hist[tid] = 0;
+    __syncthreads();
+    const uint64_t prefix = s.sel_prefix;
+    for (int i = tid; i < cnt; i += kTopkThreads) {
+      const uint64_t key = s.buf[i];
+      if ((key & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(key >> shift) & 255u], 1u);
     }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins 8l..8l+7; find the bin holding the sel_rank-th smallest
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { c[b] = s.hist[tid * 8 + b]; sum += c[b]; }
+      uint32_t incl = sum;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+      const uint32_t excl = incl - sum;
+      const uint32_t want = (uint32_t)s.sel_rank;
+      __syncwarp();
+      if (want > excl && want <= incl) {
+        uint32_t run = excl;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (want > run && want <= run + c[b]) {
+            s.sel_bin = tid * 8 + b;
+            s.sel_rank = (int)(want - run);
+            s.sel_prefix = prefix | ((uint64_t)(tid * 8 + b) << shift);
+          }
+          run += c[b];
+        }
+      }
+    }
+    mask |= (uint64_t)255u << shift;
+    __syncthreads();
+  }
+  const uint64_t kth = s.sel_prefix;
+  for (int i = tid; i < cnt; i += kTopkThreads) {
+    const uint64_t key = s.buf[i];
+    if (key <= kth) s.keep[atomicAdd(&s.keep_cnt, 1)] = key;
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += kTopkThreads) s.buf[i] = s.keep[i];
+  if (tid == 0) {
+    s.cnt = k;
+    s.thr = kth;
+    const uint32_t hi = (uint32_t)(kth >> 32);
+    s.bound = hi == 0xffffffffu ? INFINITY : raw_bound(order_key_inv(hi), r, has_scale);
   }
   __syncthreads();
 }
@@ -118,42 +162,52 @@ k_row_topk(const float* __restrict__ dist, int64_t ld, int Q, int G, int k, cons
     if (tail0 + tid < G) offer(s, INFINITY, ~0ull, row[tail0 + tid], tail0 + tid, r, has_scale);  // < 4 tail elements
     __syncthreads();
 
-    int v0 = 0;
-    bool first = true;
+    // chunk 0 is one float4 per thread so that a threshold exists early; later chunks are 4 float4 per
+    // thread, and the loads of chunk c+1 are issued before chunk c is processed (they fly across the
+    // barriers of the cut protocol)
+    float4 cur[kTopkChunkVec], nxt[kTopkChunkVec];
+    int v0 = 0, U = 1;
+#pragma unroll
+    for (int u = 0; u < kTopkChunkVec; ++u) {
+      const int v = v0 + u * kTopkThreads + tid;
+      if (u < U && v < nvec) cur[u] = ldg_stream4_topk(rv + v);
+    }
     while (v0 < nvec) {
-      // first chunk is small so that a threshold exists early; afterwards 4 x float4 per thread
-      const int U = first ? 1 : kTopkChunkVec;
-      const int chunk_elems = kTopkThreads * U * 4;
-      // everyone reads the decision inputs, then a barrier, so that no thread appends before all have read
-      const bool need = s.cnt > kTopkCap - chunk_elems || (s.thr == ~0ull && s.cnt >= max(2 * keff, 1024));
-      __syncthreads();
-      if (need) compact(s, keff, r, has_scale);
-      const float bound = s.bound;
-      const uint64_t thr = s.thr;
-      float4 x[kTopkChunkVec];
+      const int v1 = v0 + kTopkThreads * U;
+      const int Un = kTopkChunkVec;
 #pragma unroll
       for (int u = 0; u < kTopkChunkVec; ++u) {
-        const int v = v0 + u * kTopkThreads + tid;
-        if (u < U && v < nvec) x[u] = ldg_stream4_topk(rv + v);
+        const int v = v1 + u * kTopkThreads + tid;
+        if (v < nvec) nxt[u] = ldg_stream4_topk(rv + v);
       }
+      // everyone reads the decision inputs, then a barrier, so that no thread appends before all have read
+      const int chunk_elems = kTopkThreads * U * 4;
+      const bool need = s.cnt >= keff && (s.cnt > kTopkCap - chunk_elems || (s.thr == ~0ull && s.cnt >= max(2 * keff, 1024)));
+      __syncthreads();
+      if (need) cut_to_k(s, keff, r, has_scale);
+      const float bound = s.bound;
+      const uint64_t thr = s.thr;
 #pragma unroll
       for (int u = 0; u < kTopkChunkVec; ++u) {
         const int v = v0 + u * kTopkThreads + tid;
         if (u < U && v < nvec) {
           const uint32_t j = head + 4 * v;
-          offer(s, bound, thr, x[u].x, j, r, has_scale);
-          offer(s, bound, thr, x[u].y, j + 1, r, has_scale);
-          offer(s, bound, thr, x[u].z, j + 2, r, has_scale);
-          offer(s, bound, thr, x[u].w, j + 3, r, has_scale);
+          offer(s, bound, thr, cur[u].x, j, r, has_scale);
+          offer(s, bound, thr, cur[u].y, j + 1, r, has_scale);
+          offer(s, bound, thr, cur[u].z, j + 2, r, has_scale);
+          offer(s, bound, thr, cur[u].w, j + 3, r, has_scale);
         }
       }
-      v0 += kTopkThreads * U;
-      first = false;
+#pragma unroll
+      for (int u = 0; u < kTopkChunkVec; ++u) cur[u] = nxt[u];
+      v0 = v1;
+      U = Un;
       __syncthreads();
     }
-    // final: sort survivors, emit the first keff
+    // final: cut to keff, sort those few, emit
     {
       __syncthreads();
+      if (s.cnt > keff) cut_to_k(s, keff, r, has_scale);
       const int cnt = s.cnt;
       const int P = (int)next_pow2_u32((uint32_t)max(cnt, 1));
       for (int i = cnt + tid; i < P; i += kTopkThreads) s.buf[i] = ~0ull;

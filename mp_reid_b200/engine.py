@@ -28,7 +28,7 @@ def require_cuda():
 
 
 def default_precision() -> str:
-    return os.environ.get("MPREID_PRECISION", "3xtf32").lower()
+    return os.environ.get("MPREID_PRECISION", "3xfp16").lower()
 
 
 def default_junk() -> str:
@@ -47,10 +47,14 @@ class Prepared:
     hi: torch.Tensor | None      # [n, Dp] fp32 (TF32-exact)
     lo: torch.Tensor | None
     bf: torch.Tensor | None      # [n, Dp] bf16
+    hh: torch.Tensor | None = None      # [n, Dp] fp16 hi plane of the 2^s-scaled row
+    hl: torch.Tensor | None = None      # [n, Dp] fp16 lo plane
+    hscale: torch.Tensor | None = None  # [n] fp32, 2^-s
 
     def rows(self, a: int, b: int) -> "Prepared":
         s = lambda t: None if t is None else t[a:b]
-        return Prepared(b - a, self.D, self.Dp, s(self.xn), self.sqnorm[a:b], self.norm[a:b], s(self.hi), s(self.lo), s(self.bf))
+        return Prepared(b - a, self.D, self.Dp, s(self.xn), self.sqnorm[a:b], self.norm[a:b], s(self.hi), s(self.lo), s(self.bf),
+                        s(self.hh), s(self.hl), s(self.hscale))
 
 
 def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, keep_xn: bool = True) -> Prepared:
@@ -66,22 +70,27 @@ def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, ke
         x = x.contiguous()
     n, D = x.shape
     dev = x.device
-    pad = 64 if prec == L.BF16 else 32
+    pad = 64 if prec in (L.BF16, L.X3FP16) else 32
     Dp = (D + pad - 1) // pad * pad
     need_xn = keep_xn or prec == L.FP32_SIMT
     xn = torch.empty((n, D), dtype=torch.float32, device=dev) if need_xn else None
     sqnorm = torch.empty((n,), dtype=torch.float32, device=dev)
     norm = torch.empty((n,), dtype=torch.float32, device=dev)
-    hi = lo = bf = None
-    if prec == L.X3TF32:
+    hi = lo = bf = hh = hl = hscale = None
+    if prec == L.X3FP16:
+        hh = torch.empty((n, Dp), dtype=torch.float16, device=dev)
+        hl = torch.empty((n, Dp), dtype=torch.float16, device=dev)
+        hscale = torch.empty((n,), dtype=torch.float32, device=dev)
+    elif prec == L.X3TF32:
         hi = torch.empty((n, Dp), dtype=torch.float32, device=dev)
         lo = torch.empty((n, Dp), dtype=torch.float32, device=dev)
     elif prec == L.BF16:
         bf = torch.empty((n, Dp), dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.mpreid_prep_rows(x.data_ptr(), n, D, x.stride(0), int(bool(normalize)), _ptr(xn), D, sqnorm.data_ptr(),
-                                     norm.data_ptr(), _ptr(hi), _ptr(lo), _ptr(bf), Dp, _stream()), "prep_rows")
-    return Prepared(n, D, Dp, xn, sqnorm, norm, hi, lo, bf)
+                                     norm.data_ptr(), _ptr(hi), _ptr(lo), _ptr(bf), _ptr(hh), _ptr(hl), _ptr(hscale), Dp,
+                                     _stream()), "prep_rows")
+    return Prepared(n, D, Dp, xn, sqnorm, norm, hi, lo, bf, hh, hl, hscale)
 
 
 def alloc_dist(Q: int, G: int, device) -> torch.Tensor:
@@ -113,6 +122,8 @@ def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: s
         a, b, c, d, K, ldk = q.xn, None, g.xn, None, q.D, q.xn.stride(0)
     elif prec == L.X3TF32:
         a, b, c, d, K, ldk = q.hi, q.lo, g.hi, g.lo, q.Dp, q.Dp
+    elif prec == L.X3FP16:
+        a, b, c, d, K, ldk = q.hh, q.hl, g.hh, g.hl, q.Dp, q.Dp
     else:
         a, b, c, d, K, ldk = q.bf, None, g.bf, None, q.Dp, q.Dp
     if a is None or c is None:
@@ -120,7 +131,8 @@ def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: s
     if row_max is not None:
         row_max.fill_(float("-inf"))
     with torch.cuda.device(dev):
-        L.check(lib.mpreid_dist_matrix(_ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(qa), _ptr(ga), q.n, g.n, K, ldk, met, prec,
+        L.check(lib.mpreid_dist_matrix(_ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(qa), _ptr(ga), _ptr(q.hscale), _ptr(g.hscale),
+                                       q.n, g.n, K, ldk, met, prec,
                                        out.data_ptr(), out.stride(0), _ptr(row_max), _stream()), "dist_matrix")
     return out
 

@@ -46,7 +46,7 @@ def dist_tol(qn, gn):
 def test_prep_rows_normalise_norms_and_planes():
     torch.manual_seed(0)
     x = torch.randn(300, 1280, device=DEV) * 3
-    for prec in ["3xtf32", "bf16", "simt"]:
+    for prec in ["3xtf32", "3xfp16", "bf16", "simt"]:
         p = E.prep_rows(x, normalize=True, precision=prec)
         ref = torch.nn.functional.normalize(x, dim=1, p=2)
         assert torch.allclose(p.xn, ref, rtol=0, atol=2e-7)
@@ -58,6 +58,13 @@ def test_prep_rows_normalise_norms_and_planes():
             assert torch.allclose(p.hi + p.lo, p.xn, rtol=0, atol=1e-9 + 2.0 ** -21 * float(p.xn.abs().max()))
         if prec == "bf16":
             assert torch.equal(p.bf[:, :1280], p.xn.to(torch.bfloat16))
+        if prec == "3xfp16":
+            sc = 1.0 / p.hscale
+            assert torch.all(torch.log2(sc) == torch.log2(sc).round())                      # powers of two
+            mx = (p.xn.abs().max(dim=1).values * sc)
+            assert torch.all((mx >= 512) & (mx < 1024))
+            rec = (p.hh.float() + p.hl.float()) * p.hscale[:, None]
+            assert torch.allclose(rec, p.xn, rtol=0, atol=2.0 ** -21 * float(p.xn.abs().max()))
     # ragged D: zero padding up to the TMA box
     y = torch.randn(7, 100, device=DEV)
     p = E.prep_rows(y, normalize=False, precision="3xtf32")
@@ -67,7 +74,7 @@ def test_prep_rows_normalise_norms_and_planes():
 
 # ------------------------------------------------------------------------------------ distances
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("prec", ["simt", "3xtf32", "bf16"])
+@pytest.mark.parametrize("prec", ["simt", "3xtf32", "3xfp16", "bf16"])
 def test_distances_vs_reference(golden_dir, name, prec):
     g = load(golden_dir, name)
     qn, gn = norm_feats(g)
@@ -92,7 +99,7 @@ def test_tcgen05_matches_simt_on_ragged_tiles():
         q = torch.randn(Q, D, device=DEV)
         g = torch.randn(G, D, device=DEV)
         ref = (q.double() ** 2).sum(1)[:, None] + (g.double() ** 2).sum(1)[None] - 2 * q.double() @ g.double().T
-        for prec, rel in [("simt", 2e-6), ("3xtf32", 4e-6), ("bf16", 2e-2)]:
+        for prec, rel in [("simt", 2e-6), ("3xtf32", 4e-6), ("3xfp16", 4e-6), ("bf16", 2e-2)]:
             pq = E.prep_rows(q, False, prec)
             pg = E.prep_rows(g, False, prec)
             rm = torch.empty(Q, device=DEV)
@@ -219,7 +226,7 @@ def test_rerank_sparse_stages_on_reference_all_pairs_matrix(golden_dir, name, pa
         assert abs(r["mAP"] - g[tag + "_mAP"]) <= 1e-4
 
 
-@pytest.mark.parametrize("prec,tol", [("3xtf32", 1e-4), ("bf16", 5e-3)])
+@pytest.mark.parametrize("prec,tol", [("3xtf32", 1e-4), ("3xfp16", 1e-4), ("bf16", 5e-3)])
 def test_re_ranking_api_end_to_end(golden_dir, prec, tol):
     g = load(golden_dir, "rerank_small")
     qn, gn = norm_feats(g)
