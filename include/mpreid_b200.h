@@ -143,10 +143,12 @@ MPREID_API int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int
  * transposes), N = Q + G rows.  One call runs: row max + top-(k1+1) (:46-48), k-reciprocal sets
  * with the 2/3 expansion rule and the Gaussian-kernel V rows in fp16 (:51-71), k2 query expansion
  * (:73-78), inverted index (:80-82), Jaccard distance with the fp16 accumulator (:84-93) and the
- * lambda blend (:95), writing final[Q, G] fp32 (:99).  fp16 rounding points are the reference's. */
+ * lambda blend (:95), writing final[Q, G] fp32 (:99).  fp16 rounding points are the reference's.
+ * row_max_in (optional, [N]): the per-row maxima if the caller already has them (mpreid_dist_matrix
+ * produces them in its epilogue); NULL = computed here with one more pass over `dist`.            */
 MPREID_API size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, int k2);
-MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, int64_t N, int64_t Q, int k1, int k2, float lambda_value,
-                  float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
+MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
+                  float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);
 
 /* ---- host-side hooks (no GPU needed) -----------------------------------------------------------

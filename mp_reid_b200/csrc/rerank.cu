@@ -468,8 +468,8 @@ extern "C" size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, in
   return carve_rerank(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
 }
 
-extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, int64_t N, int64_t Q, int k1, int k2, float lambda_value,
-                             float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
+extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
+                             float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                              int32_t* status, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MPREID_REQUIRE(dist && final_dist && workspace, "rerank: null pointer");
@@ -488,7 +488,11 @@ extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, int64_t N, int6
   const int Keff = (int)(w.K < N ? w.K : N);
   int rc;
   // :46-48  row max (== the reference's column max in this orientation) and the first K neighbours
-  if ((rc = mpreid_row_max(dist, ld_dist, N, N, w.rowmax, stream)) != MPREID_OK) return rc;
+  if (row_max_in) {
+    MPREID_CUDA_CHECK(cudaMemcpyAsync(w.rowmax, row_max_in, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else if ((rc = mpreid_row_max(dist, ld_dist, N, N, w.rowmax, stream)) != MPREID_OK) {
+    return rc;
+  }
   if ((rc = mpreid_row_topk(dist, ld_dist, N, N, w.K, w.rowmax, w.nbr, nullptr, stream)) != MPREID_OK) return rc;
   // :51-71
   static bool attr_v0 = false, attr_jac = false;

@@ -52,21 +52,21 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n_pow2) {
   }
 }
 
-// largest raw x with fl(x / r) <= t  (r > 0, t finite); +inf when no safe bound exists
+// largest raw x with fl(x / r) <= t  (r > 0, t finite); +inf ("no filtering") when no safe bound is found.
+// x = t*r is within an ulp or two of the answer, so a few nextafter steps settle it.
 __device__ float raw_bound(float t, float r, bool has_scale) {
   if (!has_scale) return t;
   if (!(r > 0.f) || !(fabsf(t) <= 3.0e38f)) return INFINITY;
   float x = t * r;
   if (!(fabsf(x) <= 3.0e38f)) return INFINITY;
-  for (int it = 0; it < 16; ++it) {
+  int it = 0;
+  for (; it < 4 && x / r > t; ++it) x = nextafterf(x, -INFINITY);
+  if (x / r > t) return INFINITY;
+  for (it = 0; it < 4; ++it) {
     const float xn = nextafterf(x, INFINITY);
-    if (xn / r <= t) x = xn; else break;
+    if (xn / r <= t) x = xn; else return x;
   }
-  for (int it = 0; it < 16; ++it) {
-    if (x / r > t) x = nextafterf(x, -INFINITY); else break;
-  }
-  if (x / r > t || nextafterf(x, INFINITY) / r <= t) return INFINITY;  // did not converge: no filtering
-  return x;
+  return INFINITY;  // did not converge: a bound that is too small would drop candidates
 }
 
 __device__ __forceinline__ void offer(TopkSmem& s, float bound, uint64_t thr, float v, uint32_t j, float r, bool has_scale) {
@@ -112,7 +112,7 @@ __device__ void cut_to_k(TopkSmem& s, int k, float r, bool has_scale) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
           if (want > run && want <= run + c[b]) {
-            s.sel_bin = tid * 8 + b;
+            s.sel_bin = (c[b] == 1u) ? 1 : 0;          // 1 = the chosen bin holds a single key: it IS the k-th
             s.sel_rank = (int)(want - run);
             s.sel_prefix = prefix | ((uint64_t)(tid * 8 + b) << shift);
           }
@@ -122,6 +122,17 @@ __device__ void cut_to_k(TopkSmem& s, int k, float r, bool has_scale) {
     }
     mask |= (uint64_t)255u << shift;
     __syncthreads();
+    if (s.sel_bin && shift > 0) {
+      // early exit: fetch the unique key that carries the selected prefix
+      const uint64_t pfx = s.sel_prefix;
+      __syncthreads();
+      for (int i = tid; i < cnt; i += kTopkThreads) {
+        const uint64_t key = s.buf[i];
+        if ((key & mask) == pfx) s.sel_prefix = key;
+      }
+      __syncthreads();
+      break;
+    }
   }
   const uint64_t kth = s.sel_prefix;
   for (int i = tid; i < cnt; i += kTopkThreads) {

@@ -235,7 +235,7 @@ def row_max(dist: torch.Tensor) -> torch.Tensor:
 
 
 def rerank_from_dist(dist_all: torch.Tensor, query_num: int, k1: int, k2: int, lambda_value: float,
-                     out: torch.Tensor | None = None) -> torch.Tensor:
+                     out: torch.Tensor | None = None, row_max: torch.Tensor | None = None) -> torch.Tensor:
     """utils/reranking.py:45-99 on an all-pairs matrix in the orientation dist_all[i][j] = distmat[j][i]."""
     require_cuda()
     lib = L.load()
@@ -250,6 +250,6 @@ def rerank_from_dist(dist_all: torch.Tensor, query_num: int, k1: int, k2: int, l
         raise ValueError(f"re_ranking: unsupported arguments N={N} Q={query_num} k1={k1} k2={k2}")
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.mpreid_rerank(dist_all.data_ptr(), dist_all.stride(0), N, query_num, k1, k2, float(lambda_value),
+        L.check(lib.mpreid_rerank(dist_all.data_ptr(), dist_all.stride(0), _ptr(row_max), N, query_num, k1, k2, float(lambda_value),
                                   out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, None, _stream()), "rerank")
     return out

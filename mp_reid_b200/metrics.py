@@ -27,6 +27,18 @@ def _device():
     return torch.device(os.environ.get("MPREID_DEVICE", f"cuda:{torch.cuda.current_device()}"))
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    """One upload stream per device for the life of the process (a fresh stream per evaluator would
+    get a fresh caching-allocator pool, i.e. a cudaMalloc per evaluation)."""
+    key = (dev.type, dev.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 def _to_device(x, dev):
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(np.asarray(x))
@@ -132,7 +144,12 @@ def clipstyle_eval(distmat, q_pids, g_pids, q_camids, g_camids):
 
 
 class R1_mAP_eval():
-    """utils/metrics.py:91-134.  Features stay on the GPU between update() and compute()."""
+    """utils/metrics.py:91-134.  Features stay on the GPU between update() and compute().
+
+    Host batches are uploaded on a side stream as they arrive (update), and compute() consumes the
+    gallery in chunks of >= MPREID_CHUNK_ROWS rows: while chunk c is normalised and contracted against
+    the queries, chunks c+1.. are still in flight over PCIe.
+    """
 
     def __init__(self, num_query, max_rank=50, feat_norm=True, reranking=False, *, precision=None, junk=None,
                  metric="sqeuclid"):
@@ -149,6 +166,7 @@ class R1_mAP_eval():
         self.feats = []
         self.pids = []
         self.camids = []
+        self._events = []
 
     def update(self, output):  # called once for each batch
         feat, pid, camid = output
@@ -156,27 +174,100 @@ class R1_mAP_eval():
         dev = _device()
         if not isinstance(feat, torch.Tensor):
             feat = torch.as_tensor(np.asarray(feat))
+        feat = feat.detach()
         # the reference does feat.cpu() here (a synchronising D2H per batch, utils/metrics.py:106)
-        feats.append(feat.detach().to(dev, dtype=torch.float32, non_blocking=True))
+        if feat.is_cuda:
+            feats.append(feat.to(dev, dtype=torch.float32))
+            self._events.append(None)
+        else:
+            cs = _copy_stream(dev)
+            with torch.cuda.stream(cs):
+                t = feat.to(dev, dtype=torch.float32, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            feats.append(t)
+            self._events.append(ev)
         self.pids.extend(np.asarray(pid))
         self.camids.extend(np.asarray(camid))
 
+    def _wait(self, lo, hi):
+        cur = torch.cuda.current_stream()
+        for ev in self._events[lo:hi]:
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def _split_rows(self):
+        """(batch index, tensor view) lists for the query rows and the gallery rows."""
+        nq = self.num_query
+        q_parts, g_parts, row = [], [], 0
+        for bi, t in enumerate(self.feats):
+            n = t.shape[0]
+            if row + n <= nq:
+                q_parts.append((bi, t))
+            elif row >= nq:
+                g_parts.append((bi, t))
+            else:
+                q_parts.append((bi, t[: nq - row]))
+                g_parts.append((bi, t[nq - row:]))
+            row += n
+        return q_parts, g_parts
+
     def compute(self):  # called after each epoch
-        feats = torch.cat(self.feats, dim=0)
         if self.feat_norm:
             print("The test feature is normalized")
-        prep = E.prep_rows(feats, normalize=bool(self.feat_norm), precision=self._precision, keep_xn=True)
         nq = self.num_query
-        q, g = prep.rows(0, nq), prep.rows(nq, prep.n)
         q_pids = np.asarray(self.pids[:nq])
         q_camids = np.asarray(self.camids[:nq])
         g_pids = np.asarray(self.pids[nq:])
         g_camids = np.asarray(self.camids[nq:])
+        norm = bool(self.feat_norm)
         if self.reranking:
             print('=> Enter reranking')
+            self._wait(0, len(self.feats))
+            prep = E.prep_rows(torch.cat(self.feats, dim=0), normalize=norm, precision=self._precision, keep_xn=True)
+            q, g = prep.rows(0, nq), prep.rows(nq, prep.n)
             dist = _rerank_device(prep, nq, k1=50, k2=15, lambda_value=0.3, precision=self._precision)  # utils/metrics.py:127
+            qf, gf = q.xn, g.xn
         else:
             print('=> Computing DistMat with euclidean_distance')
-            dist = E.dist_matrix(q, g, self._metric, self._precision)
+            q_parts, g_parts = self._split_rows()
+            num_g = sum(t.shape[0] for _, t in g_parts)
+            self._wait(0, (q_parts[-1][0] + 1) if q_parts else 0)
+            q = E.prep_rows(torch.cat([t for _, t in q_parts], dim=0) if len(q_parts) != 1 else q_parts[0][1],
+                            normalize=norm, precision=self._precision, keep_xn=True)
+            dist = E.alloc_dist(nq, num_g, q.sqnorm.device)
+            chunk_rows = int(os.environ.get("MPREID_CHUNK_ROWS", "8192"))
+            # gallery chunks: >= chunk_rows rows each, cut at multiples of 32 rows so that every column
+            # block of the distance matrix starts 128-byte aligned (vector stores); batches are split by view
+            gf_parts, off = [], 0
+            pend, pend_rows, last_bi = [], 0, -1
+
+            def flush(rows_out):
+                nonlocal pend, pend_rows, off
+                take, got, rest = [], 0, []
+                for t in pend:
+                    if got + t.shape[0] <= rows_out:
+                        take.append(t); got += t.shape[0]
+                    elif got < rows_out:
+                        take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
+                    else:
+                        rest.append(t)
+                blk = take[0] if len(take) == 1 else torch.cat(take, dim=0)
+                g = E.prep_rows(blk, normalize=norm, precision=self._precision, keep_xn=True)
+                E.dist_matrix(q, g, self._metric, self._precision, out=dist[:, off:off + rows_out])
+                gf_parts.append(g.xn)
+                off += rows_out
+                pend, pend_rows = rest, pend_rows - rows_out
+
+            for bi, t in g_parts:
+                self._wait(last_bi + 1, bi + 1)
+                last_bi = bi
+                pend.append(t); pend_rows += t.shape[0]
+                while pend_rows >= chunk_rows:
+                    flush(pend_rows // 32 * 32 if pend_rows // 32 * 32 >= chunk_rows else pend_rows)
+            if pend_rows:
+                flush(pend_rows)
+            qf = q.xn
+            gf = gf_parts[0] if len(gf_parts) == 1 else torch.cat(gf_parts, dim=0)
         cmc, mAP = _eval_device(dist, q_pids, g_pids, q_camids, g_camids, 50, self._junk)  # :132 (max_rank is not forwarded)
-        return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, q.xn, g.xn
+        return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, qf, gf

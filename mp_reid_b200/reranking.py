@@ -18,20 +18,24 @@ def _device():
     return torch.device(os.environ.get("MPREID_DEVICE", f"cuda:{torch.cuda.current_device()}"))
 
 
-def _all_pairs(prep: E.Prepared, precision=None) -> torch.Tensor:
-    """utils/reranking.py:36-41: squared distances of the stacked features against themselves."""
+def _all_pairs(prep: E.Prepared, precision=None, row_max: torch.Tensor | None = None) -> torch.Tensor:
+    """utils/reranking.py:36-41: squared distances of the stacked features against themselves
+    (+ the per-row maxima of :46, taken in the GEMM epilogue)."""
     n = prep.n
     ld = (n + 31) // 32 * 32
     buf = torch.empty((n, ld), dtype=torch.float32, device=prep.sqnorm.device)[:, :n]
-    return E.dist_matrix(prep, prep, "sqeuclid", precision, out=buf)
+    return E.dist_matrix(prep, prep, "sqeuclid", precision, out=buf, row_max=row_max)
 
 
 def _rerank_device(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_value: float, precision=None,
                    local_distmat: torch.Tensor | None = None) -> torch.Tensor:
-    dall = _all_pairs(prep, precision)
     if local_distmat is not None:  # :43-44  (orientation: ours is the transpose of the reference's)
+        dall = _all_pairs(prep, precision)
         dall.add_(local_distmat.t())
-    return E.rerank_from_dist(dall, query_num, k1, k2, lambda_value)
+        return E.rerank_from_dist(dall, query_num, k1, k2, lambda_value)
+    row_max = torch.empty((prep.n,), dtype=torch.float32, device=prep.sqnorm.device)
+    dall = _all_pairs(prep, precision, row_max)
+    return E.rerank_from_dist(dall, query_num, k1, k2, lambda_value, row_max=row_max)
 
 
 def re_ranking(probFea, galFea, k1, k2, lambda_value, local_distmat=None, only_local=False, *, precision=None):
