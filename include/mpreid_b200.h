@@ -147,6 +147,27 @@ MPREID_API int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int
  * row_max_in (optional, [N]): the per-row maxima if the caller already has them (mpreid_dist_matrix
  * produces them in its epilogue); NULL = computed here with one more pass over `dist`.            */
 MPREID_API size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, int k2);
+/* The same pipeline in stages, for row-sharded multi-GPU runs (the one exchange step of this path:
+ * neighbour lists and V0 rows are all-gathered between the stages):
+ *   1. per rank, on its block of rows of the all-pairs matrix: mpreid_row_max / mpreid_row_topk
+ *      with k = mpreid_rerank_neighbor_count(k1, k2)                                    (:46-48)
+ *   2. mpreid_rerank_build_v0: V0 rows (ELL, capacity mpreid_rerank_v0_capacity per row) of the
+ *      rank's rows; row_ids[R] = global sample index of every local row (NULL = 0..R-1); needs the
+ *      neighbour lists of ALL samples                                                    (:51-71)
+ *   3. mpreid_rerank_finish: query expansion + inverted index over all samples (cheap, done
+ *      redundantly on every rank), Jaccard + blend for the rank's Qs query rows: dist_qrows[Qs, N]
+ *      are those rows of the all-pairs matrix, q_ids[Qs] their global indices (NULL = 0..Qs-1),
+ *      row_max_q[Qs] their maxima; writes final[Qs, N-Q]                                (:73-99)   */
+MPREID_API int mpreid_rerank_neighbor_count(int k1, int k2);
+MPREID_API int mpreid_rerank_v0_capacity(int k1, int64_t N);
+MPREID_API int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, const int32_t* row_ids, int64_t R, int64_t N,
+                           int k1, const int32_t* nbr_all, int K, const float* row_max_rows,
+                           int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream);
+MPREID_API size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int k1, int k2);
+MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                         const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
+                         int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                         float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);

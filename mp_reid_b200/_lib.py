@@ -38,6 +38,11 @@ SIGNATURES = {
     "mpreid_row_max": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "mpreid_rerank_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mpreid_rerank": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p, _p]),
+    "mpreid_rerank_neighbor_count": (_i32, [_i32, _i32]),
+    "mpreid_rerank_v0_capacity": (_i32, [_i32, _i64]),
+    "mpreid_rerank_build_v0": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p]),
+    "mpreid_rerank_finish_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "mpreid_rerank_finish": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p]),
     "mpreid_host_average_precision": (C.c_double, [_p, _i32, _i64]),
     "mpreid_host_order_keys": (None, [_p, _i64, _p]),
 }

@@ -31,51 +31,7 @@ HD int64_t v_capacity(int k1, int k2, int64_t N) {
   return c < N ? c : N;
 }
 
-struct RerankWs {
-  float* rowmax;      // [N]
-  int32_t* nbr;       // [N, K]
-  int32_t* v0_col; uint16_t* v0_val; int32_t* v0_len;   // ELL [N, C0]
-  int32_t* v_col;  uint16_t* v_val;  int32_t* v_len;    // ELL [N, C1] (aliases v0 when k2 == 1)
-  int32_t* col_cnt; int32_t* col_fill; int64_t* col_off; // [N], [N], [N+1]
-  int32_t* csc_row; uint16_t* csc_val;                   // [(N-Q) * C1]
-  uint64_t* qe_scratch;                                  // [qe_grid * qe_P]
-  int K, C0; int64_t C1; int qe_grid; int64_t qe_P;
-};
-
 static constexpr int kQeSmemEntries = 4096;
-
-static size_t carve_rerank(RerankWs* w, char* base, int64_t N, int64_t Q, int k1, int k2, int sms) {
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
-  const int K = (k1 + 1) > k2 ? (k1 + 1) : k2;
-  const int C0 = v0_capacity(k1, N);
-  const int64_t C1 = v_capacity(k1, k2, N);
-  const int qe_grid = sms * 4;
-  int64_t qe_P = 1;
-  while (qe_P < (int64_t)k2 * C0) qe_P <<= 1;
-  if (qe_P <= kQeSmemEntries || k2 == 1) qe_P = 0;  // fits shared memory: no global scratch
-  char* p;
-  p = take(N * 4); if (w) w->rowmax = (float*)p;
-  p = take(N * (size_t)K * 4); if (w) w->nbr = (int32_t*)p;
-  p = take(N * (size_t)C0 * 4); if (w) w->v0_col = (int32_t*)p;
-  p = take(N * (size_t)C0 * 2); if (w) w->v0_val = (uint16_t*)p;
-  p = take(N * 4); if (w) w->v0_len = (int32_t*)p;
-  if (k2 != 1) {
-    p = take(N * (size_t)C1 * 4); if (w) w->v_col = (int32_t*)p;
-    p = take(N * (size_t)C1 * 2); if (w) w->v_val = (uint16_t*)p;
-    p = take(N * 4); if (w) w->v_len = (int32_t*)p;
-  } else if (w) {
-    w->v_col = w->v0_col; w->v_val = w->v0_val; w->v_len = w->v0_len;
-  }
-  p = take(N * 4); if (w) w->col_cnt = (int32_t*)p;
-  p = take(N * 4); if (w) w->col_fill = (int32_t*)p;
-  p = take((N + 1) * 8); if (w) w->col_off = (int64_t*)p;
-  p = take((size_t)(N - Q) * C1 * 4); if (w) w->csc_row = (int32_t*)p;
-  p = take((size_t)(N - Q) * C1 * 2); if (w) w->csc_val = (uint16_t*)p;
-  p = take((size_t)qe_grid * qe_P * 8); if (w) w->qe_scratch = (uint64_t*)p;
-  if (w) { w->K = K; w->C0 = C0; w->C1 = C1; w->qe_grid = qe_grid; w->qe_P = qe_P; }
-  return off;
-}
 
 // numpy float32 pairwise sum (np.sum(weight), utils/reranking.py:71), dense version
 __device__ float pairwise_sum_f32(const float* a, int n) {
@@ -173,7 +129,7 @@ struct V0Smem {
 };
 
 __global__ void __launch_bounds__(kV0Threads)
-k_build_v0(const float* __restrict__ dist, int64_t ld, int N, int k1, int K, int Keff_in,
+k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ row_ids, int R, int k1, int K, int Keff_in,
            const int32_t* __restrict__ nbr, const float* __restrict__ rowmax,
            int32_t* __restrict__ v0_col, uint16_t* __restrict__ v0_val, int32_t* __restrict__ v0_len, int C0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,7 +137,9 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, int N, int k1, int K, int
   const int tid = threadIdx.x;
   const int K1 = min(k1 + 1, Keff_in);                       // forward list length (:53)
   const int half = min(round_half_even_div2(k1) + 1, Keff_in);  // candidate list length (:60)
-  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+  // il = row of this block of the all-pairs matrix, i = the sample it belongs to (global index)
+  for (int il = blockIdx.x; il < R; il += gridDim.x) {
+    const int i = row_ids ? row_ids[il] : il;
     if (tid == 0) { s.n_recip = 0; s.n_list = 0; }
     for (int m = tid; m < K1; m += kV0Threads) s.fwd[m] = nbr[(int64_t)i * K + m];
     __syncthreads();
@@ -241,8 +199,8 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, int N, int k1, int K, int
     }
     __syncthreads();
     const int nU = s.n_out;
-    const float rmax = rowmax[i];
-    const float* drow = dist + (int64_t)i * ld;
+    const float rmax = rowmax[il];
+    const float* drow = dist + (int64_t)il * ld;
     for (int t = tid; t < nU; t += kV0Threads) {
       const float dn = drow[s.list[t]] / rmax;          // original_dist[i, idx]  (:46)
       s.w[t] = (float)exp((double)(-dn));               // np.exp on float32      (:70)
@@ -267,12 +225,12 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, int N, int k1, int K, int
       int total;
       const int pos = block_exclusive_scan(keep, s.sh, &total);
       if (keep) {
-        v0_col[(int64_t)i * C0 + written + pos] = s.list[t];
-        v0_val[(int64_t)i * C0 + written + pos] = hv;
+        v0_col[(int64_t)il * C0 + written + pos] = s.list[t];
+        v0_val[(int64_t)il * C0 + written + pos] = hv;
       }
       written += total;
     }
-    if (tid == 0) v0_len[i] = written;
+    if (tid == 0) v0_len[il] = written;
     __syncthreads();
   }
 }
@@ -411,7 +369,7 @@ __global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, cons
 static constexpr int kJacThreads = 512;
 
 __global__ void __launch_bounds__(kJacThreads)
-k_jaccard(const float* __restrict__ dist, int64_t ld, int N, int Q, float lambda_value,
+k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ q_ids, int Qs, int N, int Q, float lambda_value,
           const float* __restrict__ rowmax,
           const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
           const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
@@ -422,11 +380,12 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, int N, int Q, float lambda
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
   const __half h_one = __float2half_rn(1.f), h_two = __float2half_rn(2.f);
-  for (int i = blockIdx.x; i < Q; i += gridDim.x) {
+  for (int il = blockIdx.x; il < Qs; il += gridDim.x) {
+    const int i = q_ids ? q_ids[il] : il;     // global query index: selects the V row; il selects the distance / output row
     const int len = v_len[i];
-    const float rmax = rowmax[i];
-    const float* drow = dist + (int64_t)i * ld + Q;
-    float* orow = final_dist + (int64_t)i * ld_final;
+    const float rmax = rowmax[il];
+    const float* drow = dist + (int64_t)il * ld + Q;
+    float* orow = final_dist + (int64_t)il * ld_final;
     for (int t0 = 0; t0 < G; t0 += tile_cols) {
       const int tn = min(tile_cols, G - t0);
       for (int c = tid; c < tn; c += kJacThreads) acc[c] = __float2half_rn(0.f);
@@ -463,9 +422,135 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, int N, int Q, float lambda
 
 using namespace mpreid;
 
+namespace mpreid {
+
+struct FinishWs {
+  int32_t* v_col; uint16_t* v_val; int32_t* v_len;       // ELL [N, C1] (unused when k2 == 1)
+  int32_t* col_cnt; int32_t* col_fill; int64_t* col_off; // [N], [N], [N+1]
+  int32_t* csc_row; uint16_t* csc_val;                   // [(N-Q) * C1]
+  uint64_t* qe_scratch;                                  // [qe_grid * qe_P]
+  int C0; int64_t C1; int qe_grid; int64_t qe_P;
+};
+
+static size_t carve_finish(FinishWs* w, char* base, int64_t N, int64_t Q, int k1, int k2, int sms) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
+  const int C0 = v0_capacity(k1, N);
+  const int64_t C1 = v_capacity(k1, k2, N);
+  const int qe_grid = sms * 4;
+  int64_t qe_P = 1;
+  while (qe_P < (int64_t)k2 * C0) qe_P <<= 1;
+  if (qe_P <= kQeSmemEntries || k2 == 1) qe_P = 0;  // fits shared memory: no global scratch
+  char* p;
+  if (k2 != 1) {
+    p = take(N * (size_t)C1 * 4); if (w) w->v_col = (int32_t*)p;
+    p = take(N * (size_t)C1 * 2); if (w) w->v_val = (uint16_t*)p;
+    p = take(N * 4); if (w) w->v_len = (int32_t*)p;
+  }
+  p = take(N * 4); if (w) w->col_cnt = (int32_t*)p;
+  p = take(N * 4); if (w) w->col_fill = (int32_t*)p;
+  p = take((N + 1) * 8); if (w) w->col_off = (int64_t*)p;
+  p = take((size_t)(N - Q) * C1 * 4); if (w) w->csc_row = (int32_t*)p;
+  p = take((size_t)(N - Q) * C1 * 2); if (w) w->csc_val = (uint16_t*)p;
+  p = take((size_t)qe_grid * qe_P * 8); if (w) w->qe_scratch = (uint64_t*)p;
+  if (w) { w->C0 = C0; w->C1 = C1; w->qe_grid = qe_grid; w->qe_P = qe_P; }
+  return off;
+}
+
+static int neighbor_count(int k1, int k2) { return (k1 + 1) > k2 ? (k1 + 1) : k2; }
+
+}  // namespace mpreid
+
+extern "C" int mpreid_rerank_neighbor_count(int k1, int k2) { return neighbor_count(k1, k2); }
+extern "C" int mpreid_rerank_v0_capacity(int k1, int64_t N) { return (k1 < 1 || k1 > kMaxK1 || N < 1) ? 0 : v0_capacity(k1, N); }
+
+extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, const int32_t* row_ids, int64_t R, int64_t N,
+                                      int k1, const int32_t* nbr_all, int K, const float* row_max_rows,
+                                      int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream) {
+  MPREID_REQUIRE(dist_rows && nbr_all && row_max_rows && v0_col && v0_val && v0_len, "rerank_build_v0: null pointer");
+  MPREID_REQUIRE(R > 0 && N > 1 && R <= N && N < INT32_MAX && ld_dist >= N, "rerank_build_v0: bad shape R=%lld N=%lld", (long long)R, (long long)N);
+  MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && K >= k1 + 1, "rerank_build_v0: k1 must be in [1, %d] and K >= k1+1", kMaxK1);
+  const int sms = sm_count_of_current_device();
+  static bool attr_v0 = false;
+  const int v0_smem = (int)sizeof(V0Smem);
+  if (!attr_v0) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
+    attr_v0 = true;
+  }
+  const int Keff = (int)(K < N ? K : N);
+  const int64_t grid = R < (int64_t)sms * 16 ? R : (int64_t)sms * 16;
+  k_build_v0<<<(unsigned)grid, kV0Threads, v0_smem, (cudaStream_t)stream>>>(dist_rows, ld_dist, row_ids, (int)R, k1, K, Keff, nbr_all,
+                                                                            row_max_rows, v0_col, v0_val, v0_len, v0_capacity(k1, N));
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int k1, int k2) {
+  if (N <= 1 || Q <= 0 || Q >= N || k1 < 1 || k1 > kMaxK1 || k2 < 1 || k2 > 64) return 0;
+  return carve_finish(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
+}
+
+extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                                    const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
+                                    int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                                    float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_qrows && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
+  MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= N && ld_final >= N - Q,
+                 "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
+  MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && k2 >= 1 && k2 <= 64 && K >= neighbor_count(k1, k2), "rerank_finish: bad k1/k2/K");
+  MPREID_REQUIRE(((uintptr_t)workspace & 255) == 0, "rerank_finish: workspace must be 256-byte aligned");
+  const int sms = sm_count_of_current_device();
+  if (workspace_bytes < carve_finish(nullptr, nullptr, N, Q, k1, k2, sms)) {
+    set_error("rerank_finish: workspace too small (%zu bytes)", workspace_bytes);
+    return MPREID_ERR_WORKSPACE;
+  }
+  FinishWs w;
+  memset(&w, 0, sizeof(w));
+  carve_finish(&w, (char*)workspace, N, Q, k1, k2, sms);
+  const int Keff = (int)(K < N ? K : N);
+  const int32_t* v_col = v0_col; const uint16_t* v_val = v0_val; const int32_t* v_len = v0_len;
+  // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
+  if (k2 != 1) {
+    const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
+    k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2 < Keff ? k2 : Keff, nbr_all, v0_col, v0_val, v0_len, w.C0,
+                                                             w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P);
+    v_col = w.v_col; v_val = w.v_val; v_len = w.v_len;
+  }
+  // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
+  k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
+  const int rows_per_cta = 8;
+  const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
+  k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, w.C1, w.col_cnt);
+  k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
+  k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
+  // :84-99
+  const int64_t G = N - Q;
+  int tile_cols = (int)(G < 100 * 1024 ? G : 100 * 1024);
+  tile_cols = (tile_cols + 7) & ~7;
+  const int jac_smem = tile_cols * 2;
+  static bool attr_jac = false;
+  if (!attr_jac) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 * 2));
+    attr_jac = true;
+  }
+  const int ctas_per_sm = jac_smem <= 48 * 1024 ? 4 : (jac_smem <= 100 * 1024 ? 2 : 1);
+  const int64_t jac_grid = Qs < (int64_t)sms * ctas_per_sm ? Qs : (int64_t)sms * ctas_per_sm;
+  k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist_qrows, ld_dist, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
+                                                               v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                               ld_final, tile_cols);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+// single-GPU convenience: neighbours + V0 rows + finish on the whole matrix
 extern "C" size_t mpreid_rerank_workspace_bytes(int64_t N, int64_t Q, int k1, int k2) {
-  if (N <= 0 || Q <= 0 || Q >= N || k1 < 1 || k1 > kMaxK1 || k2 < 1) return 0;
-  return carve_rerank(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
+  if (N <= 1 || Q <= 0 || Q >= N || k1 < 1 || k1 > kMaxK1 || k2 < 1 || k2 > 64) return 0;
+  const int K = neighbor_count(k1, k2), C0 = v0_capacity(k1, N);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { off = align_up(off + bytes, 256); };
+  take(N * 4); take(N * (size_t)K * 4); take(N * (size_t)C0 * 4); take(N * (size_t)C0 * 2); take(N * 4);
+  return off + mpreid_rerank_finish_workspace_bytes(N, Q, k1, k2);
 }
 
 extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
@@ -478,62 +563,33 @@ extern "C" int mpreid_rerank(const float* dist, int64_t ld_dist, const float* ro
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1, "rerank: k1 must be in [1, %d]", kMaxK1);
   MPREID_REQUIRE(k2 >= 1 && k2 <= 64, "rerank: k2 must be in [1, 64]");
   MPREID_REQUIRE(((uintptr_t)workspace & 255) == 0, "rerank: workspace must be 256-byte aligned");
-  const int sms = sm_count_of_current_device();
-  if (workspace_bytes < carve_rerank(nullptr, nullptr, N, Q, k1, k2, sms)) {
-    set_error("rerank: workspace too small (%zu bytes)", workspace_bytes);
+  const size_t need = mpreid_rerank_workspace_bytes(N, Q, k1, k2);
+  if (need == 0 || workspace_bytes < need) {
+    set_error("rerank: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return MPREID_ERR_WORKSPACE;
   }
-  RerankWs w;
-  carve_rerank(&w, (char*)workspace, N, Q, k1, k2, sms);
-  const int Keff = (int)(w.K < N ? w.K : N);
+  const int K = neighbor_count(k1, k2), C0 = v0_capacity(k1, N);
+  char* base = (char*)workspace;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base + off; off = align_up(off + bytes, 256); return p; };
+  float* rowmax = (float*)take(N * 4);
+  int32_t* nbr = (int32_t*)take(N * (size_t)K * 4);
+  int32_t* v0_col = (int32_t*)take(N * (size_t)C0 * 4);
+  uint16_t* v0_val = (uint16_t*)take(N * (size_t)C0 * 2);
+  int32_t* v0_len = (int32_t*)take(N * 4);
   int rc;
   // :46-48  row max (== the reference's column max in this orientation) and the first K neighbours
   if (row_max_in) {
-    MPREID_CUDA_CHECK(cudaMemcpyAsync(w.rowmax, row_max_in, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  } else if ((rc = mpreid_row_max(dist, ld_dist, N, N, w.rowmax, stream)) != MPREID_OK) {
+    MPREID_CUDA_CHECK(cudaMemcpyAsync(rowmax, row_max_in, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else if ((rc = mpreid_row_max(dist, ld_dist, N, N, rowmax, stream)) != MPREID_OK) {
     return rc;
   }
-  if ((rc = mpreid_row_topk(dist, ld_dist, N, N, w.K, w.rowmax, w.nbr, nullptr, stream)) != MPREID_OK) return rc;
+  if ((rc = mpreid_row_topk(dist, ld_dist, N, N, K, rowmax, nbr, nullptr, stream)) != MPREID_OK) return rc;
   // :51-71
-  static bool attr_v0 = false, attr_jac = false;
-  const int v0_smem = (int)sizeof(V0Smem);
-  if (!attr_v0) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
-    attr_v0 = true;
-  }
-  const int64_t v0_grid = N < (int64_t)sms * 16 ? N : (int64_t)sms * 16;
-  k_build_v0<<<(unsigned)v0_grid, kV0Threads, v0_smem, st>>>(dist, ld_dist, (int)N, k1, w.K, Keff, w.nbr, w.rowmax,
-                                                             w.v0_col, w.v0_val, w.v0_len, w.C0);
-  // :73-78
-  if (k2 != 1) {
-    const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
-    k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, w.K, k2 < Keff ? k2 : Keff, w.nbr, w.v0_col, w.v0_val,
-                                                             w.v0_len, w.C0, w.v_col, w.v_val, w.v_len, w.C1,
-                                                             w.qe_scratch, w.qe_P);
-  }
-  // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
-  k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
-  const int rows_per_cta = 8;
-  const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
-  k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, w.v_col, w.v_len, w.C1, w.col_cnt);
-  k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
-  k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, w.v_col, w.v_val, w.v_len, w.C1, w.col_off, w.col_fill,
-                                                     w.csc_row, w.csc_val);
-  // :84-99
-  const int64_t G = N - Q;
-  int tile_cols = (int)(G < 100 * 1024 ? G : 100 * 1024);
-  tile_cols = (tile_cols + 7) & ~7;
-  const int jac_smem = tile_cols * 2;
-  if (!attr_jac) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 * 2));
-    attr_jac = true;
-  }
-  const int ctas_per_sm = jac_smem <= 48 * 1024 ? 4 : (jac_smem <= 100 * 1024 ? 2 : 1);
-  const int64_t jac_grid = Q < (int64_t)sms * ctas_per_sm ? Q : (int64_t)sms * ctas_per_sm;
-  k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist, ld_dist, (int)N, (int)Q, lambda_value, w.rowmax, w.v_col, w.v_val,
-                                                               w.v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist, ld_final,
-                                                               tile_cols);
+  if ((rc = mpreid_rerank_build_v0(dist, ld_dist, nullptr, N, N, k1, nbr, K, rowmax, v0_col, v0_val, v0_len, stream)) != MPREID_OK) return rc;
+  // :73-99
+  if ((rc = mpreid_rerank_finish(nbr, K, v0_col, v0_val, v0_len, dist, ld_dist, nullptr, rowmax, N, Q, Q, k1, k2, lambda_value,
+                                 final_dist, ld_final, base + off, workspace_bytes - off, stream)) != MPREID_OK) return rc;
   if (status) MPREID_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
-  MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

@@ -51,6 +51,12 @@ class Prepared:
     hl: torch.Tensor | None = None      # [n, Dp] fp16 lo plane
     hscale: torch.Tensor | None = None  # [n] fp32, 2^-s
 
+    def take(self, ids: torch.Tensor) -> "Prepared":
+        """Rows `ids` (int64 device tensor) gathered into a new Prepared (used by the row-sharded re-ranking)."""
+        s = lambda t: None if t is None else t.index_select(0, ids)
+        return Prepared(int(ids.numel()), self.D, self.Dp, s(self.xn), self.sqnorm.index_select(0, ids), self.norm.index_select(0, ids),
+                        s(self.hi), s(self.lo), s(self.bf), s(self.hh), s(self.hl), s(self.hscale))
+
     def rows(self, a: int, b: int) -> "Prepared":
         s = lambda t: None if t is None else t[a:b]
         return Prepared(b - a, self.D, self.Dp, s(self.xn), self.sqnorm[a:b], self.norm[a:b], s(self.hi), s(self.lo), s(self.bf),
@@ -252,4 +258,54 @@ def rerank_from_dist(dist_all: torch.Tensor, query_num: int, k1: int, k2: int, l
     with torch.cuda.device(dev):
         L.check(lib.mpreid_rerank(dist_all.data_ptr(), dist_all.stride(0), _ptr(row_max), N, query_num, k1, k2, float(lambda_value),
                                   out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, None, _stream()), "rerank")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# staged re-ranking (row-sharded multi-GPU runs; the monolithic call above chains the same stages)
+def rerank_neighbor_count(k1: int, k2: int) -> int:
+    return int(L.load().mpreid_rerank_neighbor_count(k1, k2))
+
+
+def rerank_build_v0(dist_rows: torch.Tensor, row_ids: torch.Tensor | None, N: int, k1: int, nbr_all: torch.Tensor,
+                    row_max_rows: torch.Tensor):
+    """utils/reranking.py:51-71 for the rows of one block of the all-pairs matrix -> (col i32, val fp16 bits, len) ELL."""
+    require_cuda()
+    lib = L.load()
+    R = dist_rows.shape[0]
+    C0 = int(lib.mpreid_rerank_v0_capacity(k1, N))
+    if C0 == 0:
+        raise ValueError(f"re_ranking: unsupported k1={k1}")
+    dev = dist_rows.device
+    v0_col = torch.empty((R, C0), dtype=torch.int32, device=dev)
+    v0_val = torch.empty((R, C0), dtype=torch.float16, device=dev)  # fp16 V entries (NCCL has no int16)
+    v0_len = torch.empty((R,), dtype=torch.int32, device=dev)
+    assert nbr_all.dtype == torch.int32 and nbr_all.is_contiguous() and nbr_all.shape[0] == N
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_rerank_build_v0(dist_rows.data_ptr(), dist_rows.stride(0), _ptr(row_ids), R, N, k1, nbr_all.data_ptr(),
+                                           nbr_all.shape[1], row_max_rows.data_ptr(), v0_col.data_ptr(), v0_val.data_ptr(),
+                                           v0_len.data_ptr(), _stream()), "rerank_build_v0")
+    return v0_col, v0_val, v0_len
+
+
+def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor,
+                  N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q]."""
+    require_cuda()
+    lib = L.load()
+    v0_col, v0_val, v0_len = v0
+    Qs = dist_qrows.shape[0]
+    dev = dist_qrows.device
+    if out is None:
+        out = alloc_dist(Qs, N - Q, dev)
+    nbytes = lib.mpreid_rerank_finish_workspace_bytes(N, Q, k1, k2)
+    if nbytes == 0:
+        raise ValueError(f"re_ranking: unsupported arguments N={N} Q={Q} k1={k1} k2={k2}")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_rerank_finish(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
+                                         dist_qrows.data_ptr(), dist_qrows.stride(0), _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
+                                         k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, _stream()),
+                "rerank_finish")
     return out

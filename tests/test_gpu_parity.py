@@ -327,3 +327,69 @@ def test_market_shape_reranking_matches_reference(golden_dir):
     assert abs(float(fd.astype(np.float64).sum()) - r["final_sum"]) <= 1e-4 * r["final_sum"]
     cmc, mAP = metrics.eval_func(fd, q_pid, g_pid, q_cam, g_cam)
     assert abs(mAP - r["mAP"]) <= 1e-4 and abs(float(cmc[0]) - r["cmc"][0]) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------ chunked retrieval
+def test_chunked_retrieval_equals_single_pass_and_oracle():
+    from mp_reid_b200 import retrieval
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_set(700, 9000, 256, 300, 5, seed=21, sigma=2.0)
+    feats = orc.l2_normalize(torch.cat([qf, gf]).numpy())
+    # tiny HBM budget -> several query chunks
+    fq, fg = torch.from_numpy(feats[:700]).to(DEV), torch.from_numpy(feats[700:]).to(DEV)
+    r = retrieval.retrieve(fq, fg, q_pid, g_pid, q_cam, g_cam, k=100, feat_norm=False, block_bytes=9000 * 4 * 200)
+    assert r["chunk_rows"] < 700
+    one = retrieval.retrieve(fq, fg, q_pid, g_pid, q_cam, g_cam, k=100, feat_norm=False)
+    assert np.array_equal(r["topk"], one["topk"]) and r["mAP"] == one["mAP"] and np.array_equal(r["cmc"], one["cmc"])
+    # against the oracle on OUR distances (index work must be exact) and on the oracle's own distances (mAP close)
+    d = metrics.euclidean_distance(torch.from_numpy(feats[:700]), torch.from_numpy(feats[700:]))
+    assert np.array_equal(r["topk"], np.argsort(d, axis=1, kind="stable")[:, :100])
+    want = orc.rank_eval(d, q_pid, g_pid, q_cam, g_cam)
+    assert np.array_equal(r["ap"], want["ap"]) and r["mAP"] == want["mAP"]
+    ref = orc.rank_eval(orc.sq_euclidean(feats[:700], feats[700:]), q_pid, g_pid, q_cam, g_cam)
+    assert abs(r["mAP"] - ref["mAP"]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------ staged / sharded re-ranking
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_rerank_equals_monolithic(golden_dir, world):
+    """Several virtual ranks on ONE device: each builds its row block of the all-pairs matrix, neighbour
+    lists and V0 rows are exchanged (here: assembled in-process instead of all-gathered) and every
+    rank finishes its own query rows.  Must equal the single-call pipeline bit for bit."""
+    from mp_reid_b200 import distributed as D
+    from mp_reid_b200.reranking import _rerank_device
+    g = load(golden_dir, "rerank_small")
+    qn, gn = norm_feats(g)
+    nq = len(qn)
+    prep = E.prep_rows(dev(np.concatenate([qn, gn])), normalize=False)
+    N = prep.n
+    for (k1, k2, lam) in [(20, 6, 0.3), (7, 1, 0.3)]:
+        want = _rerank_device(prep, nq, k1, k2, lam).cpu().numpy()
+        ids_all = [D.rerank_row_ids(nq, N, world, r, DEV) for r in range(world)]
+        # pass 1: every virtual rank produces its local pieces; the "exchange" hands back the assembled global arrays
+        K = E.rerank_neighbor_count(k1, k2)
+        locals_ = []
+        for r in range(world):
+            loc = prep.take(ids_all[r])
+            rows = E.alloc_dist(loc.n, N, DEV)
+            rm = torch.empty(loc.n, device=DEV)
+            E.dist_matrix(loc, prep, "sqeuclid", out=rows, row_max=rm)
+            locals_.append((rows, rm, E.row_topk(rows, K, rm)))
+        nbr_all = torch.empty((N, K), dtype=torch.int32, device=DEV)
+        for r in range(world):
+            nbr_all[ids_all[r]] = locals_[r][2]
+        v0_loc = [E.rerank_build_v0(locals_[r][0], ids_all[r].to(torch.int32), N, k1, nbr_all, locals_[r][1]) for r in range(world)]
+        v0_all = []
+        for part in range(3):
+            full = torch.empty((N,) + tuple(v0_loc[0][part].shape[1:]), dtype=v0_loc[0][part].dtype, device=DEV)
+            for r in range(world):
+                full[ids_all[r]] = v0_loc[r][part]
+            v0_all.append(full)
+        got = np.empty_like(want)
+        for r in range(world):
+            q_lo, q_hi = D.shard_bounds(nq, world, r)
+            n_loc = q_hi - q_lo
+            rows, rm, _ = locals_[r]
+            fin = E.rerank_finish(nbr_all, tuple(v0_all), rows[:n_loc], ids_all[r][:n_loc].to(torch.int32).contiguous(), rm[:n_loc],
+                                  N, nq, k1, k2, lam)
+            got[q_lo:q_hi] = fin.cpu().numpy()
+        assert np.array_equal(got, want), (world, k1, k2)
