@@ -154,6 +154,7 @@ def run_ours(args, data, workload):
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPREID_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no version banner)
         dist.init_process_group("nccl", device_id=dev)
     qf, gf, q_pid, g_pid, q_cam, g_cam = data
     Q, G, D = qf.shape[0], gf.shape[0], qf.shape[1]

@@ -367,7 +367,21 @@ __global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, cons
 
 // ----------------------------------------------------------------------------------- Jaccard + blend
 static constexpr int kJacThreads = 512;
+static constexpr int kJacBlock = 256;      // V entries of the query row staged per round
+static constexpr int kJacMaxTile = 53248;  // fp16 accumulator entries per CTA: two CTAs per SM
 
+struct JacStage {
+  int32_t n[kJacBlock];       // inverted-list length of column k_e
+  int64_t b[kJacBlock];       // its start in the CSC arrays
+  uint16_t v[kJacBlock];      // V[i, k_e]
+};
+
+// One CTA per query row.  For every non-zero column k of V[i] (ascending: the reference's accumulation
+// order, :88-92) the gallery rows of the inverted list of k get  acc[g] = fp16(acc[g] + min(V[i,k], V[g,k])).
+// A list touches every g at most once, so a step needs no atomics, only a barrier before the next k.
+// The dependent global loads (V row -> list offsets -> list entries) are taken off the critical path:
+// the row's (k, offset, length) triples are staged in shared memory 256 at a time and every thread
+// fetches its list entry of step e+1 while step e is applied.
 __global__ void __launch_bounds__(kJacThreads)
 k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ q_ids, int Qs, int N, int Q, float lambda_value,
           const float* __restrict__ rowmax,
@@ -375,7 +389,8 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
           const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
           float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* acc = reinterpret_cast<__half*>(smem_raw);  // [tile_cols] fp16 accumulator (temp_min, :87)
+  JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
+  __half* acc = reinterpret_cast<__half*>(smem_raw + sizeof(JacStage));  // [tile_cols] fp16 accumulator (temp_min, :87)
   const int tid = threadIdx.x;
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
@@ -388,30 +403,74 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
     float* orow = final_dist + (int64_t)il * ld_final;
     for (int t0 = 0; t0 < G; t0 += tile_cols) {
       const int tn = min(tile_cols, G - t0);
-      for (int c = tid; c < tn; c += kJacThreads) acc[c] = __float2half_rn(0.f);
-      __syncthreads();
-      for (int e = 0; e < len; ++e) {           // ascending column k: the reference's accumulation order (:88-92)
-        const int32_t k = v_col[(int64_t)i * C1 + e];
-        const __half vik = __ushort_as_half(v_val[(int64_t)i * C1 + e]);
-        const int64_t b = col_off[k], n = col_off[k + 1] - b;
-        for (int64_t u = tid; u < n; u += kJacThreads) {
-          const int c = csc_row[b + u] - Q - t0;
-          if (c >= 0 && c < tn) {
-            const __half vg = __ushort_as_half(csc_val[b + u]);
-            const __half mn = __hlt(vg, vik) ? vg : vik;
-            acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
-          }
+      {
+        uint4* a4 = reinterpret_cast<uint4*>(acc);
+        const int n4 = (tn + 7) >> 3;
+        for (int c = tid; c < n4; c += kJacThreads) a4[c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int e0 = 0; e0 < len; e0 += kJacBlock) {
+        const int nb = min(kJacBlock, len - e0);
+        __syncthreads();   // previous round fully applied (and the zero fill visible) before the stage is rewritten
+        if (tid < nb) {
+          const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
+          const int64_t b = col_off[k];
+          st.b[tid] = b;
+          st.n[tid] = (int32_t)(col_off[k + 1] - b);
+          st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
         }
         __syncthreads();
+        int32_t pre_row = 0; uint16_t pre_val = 0;
+        if (tid < st.n[0]) { pre_row = csc_row[st.b[0] + tid]; pre_val = csc_val[st.b[0] + tid]; }
+        for (int e = 0; e < nb; ++e) {
+          const int n = st.n[e];
+          const int64_t b = st.b[e];
+          const __half vik = __ushort_as_half(st.v[e]);
+          const int32_t cur_row = pre_row; const uint16_t cur_val = pre_val;
+          if (e + 1 < nb && tid < st.n[e + 1]) {             // in flight while step e is applied
+            pre_row = csc_row[st.b[e + 1] + tid];
+            pre_val = csc_val[st.b[e + 1] + tid];
+          }
+          if (tid < n) {
+            const int c = cur_row - Q - t0;
+            if (c >= 0 && c < tn) {
+              const __half vg = __ushort_as_half(cur_val);
+              const __half mn = __hlt(vg, vik) ? vg : vik;
+              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+            }
+          }
+          for (int u = tid + kJacThreads; u < n; u += kJacThreads) {   // lists longer than the CTA (rare)
+            const int c = csc_row[b + u] - Q - t0;
+            if (c >= 0 && c < tn) {
+              const __half vg = __ushort_as_half(csc_val[b + u]);
+              const __half mn = __hlt(vg, vik) ? vg : vik;
+              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+            }
+          }
+          __syncthreads();
+        }
       }
-      for (int c = tid; c < tn; c += kJacThreads) {
-        const float a = __half2float(acc[c]);
-        const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
-        const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
-        const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
-        const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
-        const float dn = drow[t0 + c] / rmax;                                    // original_dist[i, Q+g]   (:46,72)
-        orow[t0 + c] = __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value)); // (:95) two roundings, no FMA contraction
+      __syncthreads();
+      // Jaccard + blend, four independent columns per thread per trip (coalesced 128-byte warp accesses)
+      for (int c0 = tid; c0 < tn; c0 += kJacThreads * 4) {
+        float dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * kJacThreads;
+          dv[j] = c < tn ? drow[t0 + c] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * kJacThreads;
+          if (c < tn) {
+            const float a = __half2float(acc[c]);
+            const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
+            const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
+            const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
+            const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
+            const float dn = dv[j] / rmax;                                           // original_dist[i, Q+g]   (:46,72)
+            orow[t0 + c] = __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value)); // (:95) two roundings, no FMA contraction
+          }
+        }
       }
       __syncthreads();
     }
@@ -526,15 +585,17 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
   k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
   // :84-99
   const int64_t G = N - Q;
-  int tile_cols = (int)(G < 100 * 1024 ? G : 100 * 1024);
+  const int64_t n_tiles = ceil_div(G, kJacMaxTile);
+  int tile_cols = (int)ceil_div(G, n_tiles);
   tile_cols = (tile_cols + 7) & ~7;
-  const int jac_smem = tile_cols * 2;
+  const int jac_smem = (int)sizeof(JacStage) + tile_cols * 2;
   static bool attr_jac = false;
   if (!attr_jac) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 * 2));
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(JacStage) + kJacMaxTile * 2 + 16));
     attr_jac = true;
   }
-  const int ctas_per_sm = jac_smem <= 48 * 1024 ? 4 : (jac_smem <= 100 * 1024 ? 2 : 1);
+  const int ctas_per_sm = jac_smem <= 24 * 1024 ? 4 : (jac_smem <= 54 * 1024 ? 3 : 2);
   const int64_t jac_grid = Qs < (int64_t)sms * ctas_per_sm ? Qs : (int64_t)sms * ctas_per_sm;
   k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist_qrows, ld_dist, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
                                                                v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,

@@ -15,41 +15,15 @@
 namespace mpreid {
 
 static constexpr int kTopkThreads = 256;
-static constexpr int kTopkCap = 6144;       // candidate buffer entries (48 KB)
-static constexpr int kTopkChunkVec = 4;     // float4 loads per thread per chunk
+static constexpr int kTopkWarps = kTopkThreads / 32;
+static constexpr int kTopkChunk = 32 * 16;  // elements one warp classifies per trip (4 x float4 per lane)
 static constexpr int kTopkMaxK = 2048;
-
-struct TopkSmem {
-  uint64_t buf[kTopkCap];
-  uint64_t keep[kTopkMaxK];   // survivors of a cut, staged before they move to the buffer front
-  uint32_t hist[256];
-  int cnt, keep_cnt, sel_rank, sel_bin;
-  float bound;       // raw-domain rejection bound
-  uint64_t thr;      // current k-th best key (divided domain); ~0 = none yet
-  uint64_t sel_prefix;
-};
 
 __device__ __forceinline__ float4 ldg_stream4_topk(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
-}
-
-__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n_pow2) {
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pow2; i += kTopkThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = a[i], y = a[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // largest raw x with fl(x / r) <= t  (r > 0, t finite); +inf ("no filtering") when no safe bound is found.
@@ -69,174 +43,236 @@ __device__ float raw_bound(float t, float r, bool has_scale) {
   return INFINITY;  // did not converge: a bound that is too small would drop candidates
 }
 
-__device__ __forceinline__ void offer(TopkSmem& s, float bound, uint64_t thr, float v, uint32_t j, float r, bool has_scale) {
-  if (v > bound) return;                         // NaN falls through and sorts last
-  const float dv = has_scale ? v / r : v;
-  const uint64_t key = make_key(dv, j);
-  if (key < thr) {
-    const int slot = atomicAdd(&s.cnt, 1);
-    s.buf[slot] = key;                           // capacity is guaranteed by the chunk protocol
+// ---- warp-level selection over a shared-memory array of unique 64-bit keys (no block barriers) ----
+struct WarpSel {
+  uint64_t* q;      // [cap] candidate buffer of this warp
+  uint32_t* hist;   // [256]
+  int lane;
+};
+
+// k-th smallest (1-based) of q[0..count): MSB-first radix select, 8 bits per pass, early exit once the
+// selected bin holds a single key
+__device__ uint64_t warp_select_kth(const WarpSel& w, int count, int k) {
+  uint64_t prefix = 0, mask = 0;
+  uint32_t want = (uint32_t)k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) w.hist[w.lane * 8 + b] = 0;
+    __syncwarp();
+    for (int e = w.lane; e < count; e += 32) {
+      const uint64_t key = w.q[e];
+      if ((key & mask) == prefix) atomicAdd(&w.hist[(uint32_t)(key >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { c[b] = w.hist[w.lane * 8 + b]; sum += c[b]; }
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (w.lane >= o) incl += y; }
+    const uint32_t excl = incl - sum;
+    const bool mine = want > excl && want <= incl;
+    uint32_t bin = 0, rest = 0, bcount = 0;
+    if (mine) {
+      uint32_t run = excl;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (want > run && want <= run + c[b]) { bin = w.lane * 8 + b; rest = want - run; bcount = c[b]; }
+        run += c[b];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    want = __shfl_sync(0xffffffffu, rest, src);
+    bcount = __shfl_sync(0xffffffffu, bcount, src);
+    prefix |= (uint64_t)bin << shift;
+    mask |= (uint64_t)255u << shift;
+    __syncwarp();
+    if (bcount == 1 && shift > 0) {   // the only key with this prefix is the answer
+      uint64_t found = 0;
+      for (int e0 = 0; e0 < count; e0 += 32) {
+        const int e = e0 + w.lane;
+        const uint64_t key = e < count ? w.q[e] : ~0ull;
+        const bool hit = e < count && (key & mask) == prefix;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) { found = __shfl_sync(0xffffffffu, key, __ffs(bal) - 1); break; }
+      }
+      return found;
+    }
+  }
+  return prefix;
+}
+
+// keep the entries of q[from..count) for which pred(key) holds, compacted (in order) to q[to..]; returns the new count
+template <class Pred>
+__device__ int warp_compact(const WarpSel& w, int from, int count, int to, Pred pred) {
+  int out = to;
+  for (int e0 = from; e0 < count; e0 += 32) {
+    const int e = e0 + w.lane;
+    uint64_t key = e < count ? w.q[e] : 0ull;
+    bool keep = e < count;
+    if (keep) keep = pred(key);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) w.q[out + __popc(bal & ((1u << w.lane) - 1u))] = key;
+    out += __popc(bal);
+    __syncwarp();
+  }
+  return out;
+}
+
+__device__ void warp_bitonic(const WarpSel& w, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = w.lane; i < n_pow2; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = w.q[i], y = w.q[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { w.q[i] = y; w.q[ixj] = x; }
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
-// Cut the candidate buffer back to its k smallest keys WITHOUT sorting it: MSB-first radix select
-// (8 bits per pass, shared-memory histogram) finds the k-th smallest 64-bit key, then one sweep
-// keeps the keys <= it (keys are unique, so exactly k survive).  All threads call; cnt >= k >= 1.
-__device__ void cut_to_k(TopkSmem& s, int k, float r, bool has_scale) {
-  const int tid = threadIdx.x;
-  __syncthreads();
-  const int cnt = s.cnt;
-  if (tid == 0) { s.sel_prefix = 0; s.sel_rank = k; s.keep_cnt = 0; }
-  uint64_t mask = 0;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    s.hist[tid] = 0;
-    __syncthreads();
-    const uint64_t prefix = s.sel_prefix;
-    for (int i = tid; i < cnt; i += kTopkThreads) {
-      const uint64_t key = s.buf[i];
-      if ((key & mask) == prefix) atomicAdd(&s.hist[(uint32_t)(key >> shift) & 255u], 1u);
+// One WARP per row, no block-level barrier anywhere.  q[0..nkeys) holds survivors as sort keys
+// (ordered value bits << 32 | column); q[nkeys..count) holds raw entries (column << 32 | float bits)
+// appended by the streaming loop.  cut(): raw -> key (exact IEEE division by the row scale), drop what
+// no longer beats the threshold, and if more than k remain select the k smallest.
+struct RowState {
+  int count, nkeys;
+  uint64_t thr;   // current k-th best key, ~0 = none yet
+  float bound;    // raw-domain rejection bound
+};
+
+__device__ void warp_cut(const WarpSel& w, RowState& st, int k, float r, bool has_scale) {
+  const uint64_t thr = st.thr;
+  // convert + filter the raw tail in place
+  int out = st.nkeys;
+  for (int e0 = st.nkeys; e0 < st.count; e0 += 32) {
+    const int e = e0 + w.lane;
+    uint64_t key = 0;
+    bool keep = false;
+    if (e < st.count) {
+      const uint64_t raw = w.q[e];
+      const float v = __uint_as_float((uint32_t)(raw & 0xffffffffu));
+      key = make_key(has_scale ? v / r : v, (uint32_t)(raw >> 32));
+      keep = key < thr;
     }
-    __syncthreads();
-    if (tid < 32) {
-      // lane l owns bins 8l..8l+7; find the bin holding the sel_rank-th smallest
-      uint32_t c[8], sum = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) { c[b] = s.hist[tid * 8 + b]; sum += c[b]; }
-      uint32_t incl = sum;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
-      const uint32_t excl = incl - sum;
-      const uint32_t want = (uint32_t)s.sel_rank;
-      __syncwarp();
-      if (want > excl && want <= incl) {
-        uint32_t run = excl;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (want > run && want <= run + c[b]) {
-            s.sel_bin = (c[b] == 1u) ? 1 : 0;          // 1 = the chosen bin holds a single key: it IS the k-th
-            s.sel_rank = (int)(want - run);
-            s.sel_prefix = prefix | ((uint64_t)(tid * 8 + b) << shift);
-          }
-          run += c[b];
-        }
-      }
-    }
-    mask |= (uint64_t)255u << shift;
-    __syncthreads();
-    if (s.sel_bin && shift > 0) {
-      // early exit: fetch the unique key that carries the selected prefix
-      const uint64_t pfx = s.sel_prefix;
-      __syncthreads();
-      for (int i = tid; i < cnt; i += kTopkThreads) {
-        const uint64_t key = s.buf[i];
-        if ((key & mask) == pfx) s.sel_prefix = key;
-      }
-      __syncthreads();
-      break;
-    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) w.q[out + __popc(bal & ((1u << w.lane) - 1u))] = key;
+    out += __popc(bal);
+    __syncwarp();
   }
-  const uint64_t kth = s.sel_prefix;
-  for (int i = tid; i < cnt; i += kTopkThreads) {
-    const uint64_t key = s.buf[i];
-    if (key <= kth) s.keep[atomicAdd(&s.keep_cnt, 1)] = key;
-  }
-  __syncthreads();
-  for (int i = tid; i < k; i += kTopkThreads) s.buf[i] = s.keep[i];
-  if (tid == 0) {
-    s.cnt = k;
-    s.thr = kth;
+  st.count = out;
+  if (st.count > k) {
+    const uint64_t kth = warp_select_kth(w, st.count, k);
+    st.count = warp_compact(w, 0, st.count, 0, [kth](uint64_t key) { return key <= kth; });
+    st.thr = kth;
     const uint32_t hi = (uint32_t)(kth >> 32);
-    s.bound = hi == 0xffffffffu ? INFINITY : raw_bound(order_key_inv(hi), r, has_scale);
+    float b = INFINITY;
+    if (w.lane == 0 && hi != 0xffffffffu) b = raw_bound(order_key_inv(hi), r, has_scale);
+    st.bound = __shfl_sync(0xffffffffu, b, 0);
   }
-  __syncthreads();
+  st.nkeys = st.count;
 }
 
 __global__ void __launch_bounds__(kTopkThreads)
 k_row_topk(const float* __restrict__ dist, int64_t ld, int Q, int G, int k, const float* __restrict__ row_scale,
-           int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+           int32_t* __restrict__ idx_out, float* __restrict__ val_out, int cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TopkSmem& s = *reinterpret_cast<TopkSmem*>(smem_raw);
-  const int tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSel w;
+  w.q = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * cap;
+  w.hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTopkWarps * cap * 8) + warp * 256;
+  w.lane = lane;
   const int keff = min(k, G);
-  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
-    const float* row = dist + (int64_t)q * ld;
-    const bool has_scale = row_scale != nullptr;
-    const float r = has_scale ? row_scale[q] : 1.0f;
-    if (tid == 0) { s.cnt = 0; s.thr = ~0ull; s.bound = INFINITY; }
-    __syncthreads();
+  const int drain_at = cap - kTopkChunk;   // cut before a full chunk could overflow the buffer
+  const bool has_scale = row_scale != nullptr;
+  for (int row_i = blockIdx.x * kTopkWarps + warp; row_i < Q; row_i += gridDim.x * kTopkWarps) {
+    const float* row = dist + (int64_t)row_i * ld;
+    const float r = has_scale ? row_scale[row_i] : 1.0f;
+    RowState st;
+    st.count = 0; st.nkeys = 0; st.thr = ~0ull; st.bound = INFINITY;
 
     int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
     head = min(head, G);
-    if (tid < head) offer(s, INFINITY, ~0ull, row[tid], tid, r, has_scale);
     const int nvec = (G - head) >> 2;
     const float4* rv = reinterpret_cast<const float4*>(row + head);
-    const int tail0 = head + 4 * nvec;
-    if (tail0 + tid < G) offer(s, INFINITY, ~0ull, row[tail0 + tid], tail0 + tid, r, has_scale);  // < 4 tail elements
-    __syncthreads();
-
-    // chunk 0 is one float4 per thread so that a threshold exists early; later chunks are 4 float4 per
-    // thread, and the loads of chunk c+1 are issued before chunk c is processed (they fly across the
-    // barriers of the cut protocol)
-    float4 cur[kTopkChunkVec], nxt[kTopkChunkVec];
-    int v0 = 0, U = 1;
-#pragma unroll
-    for (int u = 0; u < kTopkChunkVec; ++u) {
-      const int v = v0 + u * kTopkThreads + tid;
-      if (u < U && v < nvec) cur[u] = ldg_stream4_topk(rv + v);
+    {  // ragged ends (< 4 elements each)
+      uint32_t mask = 0; float v[2] = {0.f, 0.f}; uint32_t jj[2] = {0u, 0u};
+      if (lane < head) { v[0] = row[lane]; jj[0] = lane; mask |= 1u; }
+      const int t = head + 4 * nvec + lane;
+      if (t < G) { v[1] = row[t]; jj[1] = t; mask |= 2u; }
+      const int n = __popc(mask);
+      int incl = n;
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      int pos = st.count + incl - n;
+      if (mask & 1u) w.q[pos++] = ((uint64_t)jj[0] << 32) | __float_as_uint(v[0]);
+      if (mask & 2u) w.q[pos++] = ((uint64_t)jj[1] << 32) | __float_as_uint(v[1]);
+      st.count += __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
     }
-    while (v0 < nvec) {
-      const int v1 = v0 + kTopkThreads * U;
-      const int Un = kTopkChunkVec;
+    constexpr int U = 4;
+    for (int v0 = 0; v0 < nvec; v0 += 32 * U) {
+      float4 x[U];
 #pragma unroll
-      for (int u = 0; u < kTopkChunkVec; ++u) {
-        const int v = v1 + u * kTopkThreads + tid;
-        if (v < nvec) nxt[u] = ldg_stream4_topk(rv + v);
+      for (int u = 0; u < U; ++u) {
+        const int v = v0 + u * 32 + lane;
+        x[u] = v < nvec ? ldg_stream4_topk(rv + v) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       }
-      // everyone reads the decision inputs, then a barrier, so that no thread appends before all have read
-      const int chunk_elems = kTopkThreads * U * 4;
-      const bool need = s.cnt >= keff && (s.cnt > kTopkCap - chunk_elems || (s.thr == ~0ull && s.cnt >= max(2 * keff, 1024)));
-      __syncthreads();
-      if (need) cut_to_k(s, keff, r, has_scale);
-      const float bound = s.bound;
-      const uint64_t thr = s.thr;
+      const float bound = st.bound;
+      uint32_t mask = 0;
 #pragma unroll
-      for (int u = 0; u < kTopkChunkVec; ++u) {
-        const int v = v0 + u * kTopkThreads + tid;
-        if (u < U && v < nvec) {
-          const uint32_t j = head + 4 * v;
-          offer(s, bound, thr, cur[u].x, j, r, has_scale);
-          offer(s, bound, thr, cur[u].y, j + 1, r, has_scale);
-          offer(s, bound, thr, cur[u].z, j + 2, r, has_scale);
-          offer(s, bound, thr, cur[u].w, j + 3, r, has_scale);
+      for (int u = 0; u < U; ++u) {
+        mask |= (!(x[u].x > bound) ? 1u : 0u) << (4 * u);
+        mask |= (!(x[u].y > bound) ? 2u : 0u) << (4 * u);
+        mask |= (!(x[u].z > bound) ? 4u : 0u) << (4 * u);
+        mask |= (!(x[u].w > bound) ? 8u : 0u) << (4 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v0 + u * 32 + lane >= nvec) mask &= ~(0xfu << (4 * u));
+      const int n = __popc(mask);
+      int incl = n;
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        int pos = st.count + incl - n;
+        if (mask) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint64_t j = (uint64_t)(head + 4 * (v0 + u * 32 + lane));
+            if (mask & (1u << (4 * u))) w.q[pos++] = (j << 32) | __float_as_uint(x[u].x);
+            if (mask & (2u << (4 * u))) w.q[pos++] = ((j + 1) << 32) | __float_as_uint(x[u].y);
+            if (mask & (4u << (4 * u))) w.q[pos++] = ((j + 2) << 32) | __float_as_uint(x[u].z);
+            if (mask & (8u << (4 * u))) w.q[pos++] = ((j + 3) << 32) | __float_as_uint(x[u].w);
+          }
         }
+        st.count += total;
+        __syncwarp();
+        // cut when another chunk could overflow the buffer (the first cut comes after max(2k, 256) candidates)
+        if (st.count > drain_at) warp_cut(w, st, keff, r, has_scale);
       }
-#pragma unroll
-      for (int u = 0; u < kTopkChunkVec; ++u) cur[u] = nxt[u];
-      v0 = v1;
-      U = Un;
-      __syncthreads();
     }
-    // final: cut to keff, sort those few, emit
-    {
-      __syncthreads();
-      if (s.cnt > keff) cut_to_k(s, keff, r, has_scale);
-      const int cnt = s.cnt;
-      const int P = (int)next_pow2_u32((uint32_t)max(cnt, 1));
-      for (int i = cnt + tid; i < P; i += kTopkThreads) s.buf[i] = ~0ull;
-      __syncthreads();
-      bitonic_sort_smem(s.buf, P);
-      for (int i = tid; i < k; i += kTopkThreads) {
-        int32_t id = -1;
-        float val = INFINITY;
-        if (i < keff) {
-          const uint64_t key = s.buf[i];
-          id = (int32_t)(key & 0xffffffffu);
-          val = has_scale ? row[id] / r : row[id];
-        }
-        idx_out[(int64_t)q * k + i] = id;
-        if (val_out) val_out[(int64_t)q * k + i] = val;
+    warp_cut(w, st, keff, r, has_scale);
+    const int P = (int)next_pow2_u32((uint32_t)max(st.count, 1));
+    for (int i = st.count + lane; i < P; i += 32) w.q[i] = ~0ull;
+    __syncwarp();
+    warp_bitonic(w, P);
+    for (int i = lane; i < k; i += 32) {
+      int32_t id = -1;
+      float val = INFINITY;
+      if (i < keff) {
+        id = (int32_t)(w.q[i] & 0xffffffffu);
+        val = has_scale ? row[id] / r : row[id];
       }
-      __syncthreads();
+      idx_out[(int64_t)row_i * k + i] = id;
+      if (val_out) val_out[(int64_t)row_i * k + i] = val;
     }
+    __syncwarp();
   }
 }
 
@@ -276,15 +312,21 @@ extern "C" int mpreid_row_topk(const float* dist, int64_t ld_dist, int64_t Q, in
                                const float* row_scale, int32_t* idx, float* val, void* stream) {
   MPREID_REQUIRE(dist && idx && Q > 0 && G > 0 && ld_dist >= G && Q < INT32_MAX && G < INT32_MAX, "row_topk: bad arguments");
   MPREID_REQUIRE(k >= 1 && k <= kTopkMaxK, "row_topk: k must be in [1, %d], got %d", kTopkMaxK, k);
-  static bool attr_set = false;
-  const int smem = (int)sizeof(TopkSmem);
-  if (!attr_set) {
+  // per-warp candidate buffer: max(2k, 256) entries between cuts plus one full chunk
+  int cap = (2 * k > 256 ? 2 * k : 256) + kTopkChunk;
+  cap = (cap + 31) / 32 * 32;
+  const int smem = kTopkWarps * (cap * 8 + 256 * 4);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
     MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_row_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   const int sms = sm_count_of_current_device();
-  const int64_t grid = Q < (int64_t)sms * 3 ? Q : (int64_t)sms * 3;
-  k_row_topk<<<(unsigned)grid, kTopkThreads, smem, (cudaStream_t)stream>>>(dist, ld_dist, (int)Q, (int)G, k, row_scale, idx, val);
+  int ctas_per_sm = (220 * 1024) / (smem + 1024);
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t want = ceil_div(Q, kTopkWarps);
+  const int64_t grid = want < (int64_t)sms * ctas_per_sm ? want : (int64_t)sms * ctas_per_sm;
+  k_row_topk<<<(unsigned)grid, kTopkThreads, smem, (cudaStream_t)stream>>>(dist, ld_dist, (int)Q, (int)G, k, row_scale, idx, val, cap);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

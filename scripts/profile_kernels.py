@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mp_reid_b200 import engine as E, synth
 from mp_reid_b200.reranking import _rerank_device
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
+prec = sys.argv[1] if len(sys.argv) > 1 else "3xfp16"
 qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_shape("msmt17")
 dev = torch.device("cuda:0")
 feats = torch.cat([qf, gf]).to(dev)
