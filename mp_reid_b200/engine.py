@@ -152,12 +152,32 @@ def _labels(x, device) -> torch.Tensor:
 _pos_capacity_hint = {}
 
 
-def rank_eval(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: str | None = None):
-    """eval_func's per-query part (utils/metrics.py:39-80) -> (first_hit i32[Q], ap f64[Q], num_rel i32[Q]) on device.
+class RankResult:
+    """Per-query outputs of the rank/AP kernels in ONE device allocation (so that one D2H copy brings
+    everything back, status word included):  [ap f64 x Q | first_hit i32 x Q | num_rel i32 x Q | status i32 x 4]."""
 
-    Synchronises once (to read the 16-byte status word that tells whether the positives workspace
-    was large enough; it is re-run with the exact size otherwise).
-    """
+    def __init__(self, Q: int, device):
+        self.Q = Q
+        self.buf = torch.empty((16 * Q + 16,), dtype=torch.uint8, device=device)
+        self.ap = self.buf[: 8 * Q].view(torch.float64)
+        self.first_hit = self.buf[8 * Q: 12 * Q].view(torch.int32)
+        self.num_rel = self.buf[12 * Q: 16 * Q].view(torch.int32)
+        self.status = self.buf[16 * Q:].view(torch.int32)
+
+    def to_host(self):
+        """-> (first_hit, ap, num_rel, status) numpy views of one pinned host copy (synchronises)."""
+        host = torch.empty(self.buf.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(self.buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = host.numpy()
+        Q = self.Q
+        return (h[8 * Q: 12 * Q].view(np.int32), h[: 8 * Q].view(np.float64), h[12 * Q: 16 * Q].view(np.int32),
+                h[16 * Q:].view(np.int32))
+
+
+def rank_eval_async(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: str | None = None,
+                    capacity: int | None = None) -> RankResult:
+    """Launches the rank/AP kernels and returns without synchronising; check `status[0]` after the copy."""
     require_cuda()
     lib = L.load()
     junk_mode = L.JUNKS[(junk or default_junk()).lower()]
@@ -169,30 +189,50 @@ def rank_eval(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: st
         q_cam, g_cam = _labels(q_cam, dev), _labels(g_cam, dev)
     else:
         q_cam = g_cam = None
-    first_hit = torch.empty((Q,), dtype=torch.int32, device=dev)
-    ap = torch.empty((Q,), dtype=torch.float64, device=dev)
-    num_rel = torch.empty((Q,), dtype=torch.int32, device=dev)
-    status = torch.zeros((4,), dtype=torch.int32, device=dev)
-    cap = max(_pos_capacity_hint.get((Q, G), 0), 64 * Q, 1 << 16)
-    for attempt in range(2):
-        nbytes = lib.mpreid_rank_eval_workspace_bytes(Q, G, cap)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            L.check(lib.mpreid_rank_eval(dist.data_ptr(), dist.stride(0), Q, G, q_pid.data_ptr(), g_pid.data_ptr(),
-                                         _ptr(q_cam), _ptr(g_cam), junk_mode, first_hit.data_ptr(), ap.data_ptr(),
-                                         num_rel.data_ptr(), ws.data_ptr(), nbytes, cap, status.data_ptr(), _stream()),
-                    "rank_eval")
-        st = status.cpu()
-        if int(st[0]) == 0:
-            break
+    res = RankResult(Q, dev)
+    cap = capacity or max(_pos_capacity_hint.get((Q, G), 0), 64 * Q, 1 << 16)
+    nbytes = lib.mpreid_rank_eval_workspace_bytes(Q, G, cap)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_rank_eval(dist.data_ptr(), dist.stride(0), Q, G, q_pid.data_ptr(), g_pid.data_ptr(),
+                                     _ptr(q_cam), _ptr(g_cam), junk_mode, res.first_hit.data_ptr(), res.ap.data_ptr(),
+                                     res.num_rel.data_ptr(), ws.data_ptr(), nbytes, cap, res.status.data_ptr(), _stream()),
+                "rank_eval")
+    res._retry = (dist, q_pid, g_pid, q_cam, g_cam, junk)
+    return res
+
+
+def rank_eval_host(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: str | None = None):
+    """eval_func's per-query part (utils/metrics.py:39-80) -> numpy (first_hit i32[Q], ap f64[Q], num_rel i32[Q]).
+    One synchronising D2H copy; re-run with the exact workspace size if the positives workspace overflowed."""
+    res = rank_eval_async(dist, q_pid, g_pid, q_cam, g_cam, junk)
+    fh, ap, nr, st = res.to_host()
+    if int(st[0]) != 0:
         need = int(st[1])
         if need >= 2**31 - 1:
             raise L.MpreidError("rank_eval: more than 2^31 same-pid (query, gallery) pairs")
-        cap = need
-        _pos_capacity_hint[(Q, G)] = need
-    else:
-        raise L.MpreidError("rank_eval: positives workspace overflow after resize")
-    return first_hit, ap, num_rel
+        _pos_capacity_hint[tuple(dist.shape)] = need
+        res = rank_eval_async(dist, q_pid, g_pid, q_cam, g_cam, junk, capacity=need)
+        fh, ap, nr, st = res.to_host()
+        if int(st[0]) != 0:
+            raise L.MpreidError("rank_eval: positives workspace overflow after resize")
+    return fh, ap, nr
+
+
+def rank_eval(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, junk: str | None = None):
+    """Device-tensor flavour: -> (first_hit i32[Q], ap f64[Q], num_rel i32[Q]) on the device.
+    Synchronises once on the 16-byte status word (workspace overflow -> re-run with the exact size)."""
+    res = rank_eval_async(dist, q_pid, g_pid, q_cam, g_cam, junk)
+    st = res.status.cpu()
+    if int(st[0]) != 0:
+        need = int(st[1])
+        if need >= 2**31 - 1:
+            raise L.MpreidError("rank_eval: more than 2^31 same-pid (query, gallery) pairs")
+        _pos_capacity_hint[tuple(dist.shape)] = need
+        res = rank_eval_async(dist, q_pid, g_pid, q_cam, g_cam, junk, capacity=need)
+        if int(res.status.cpu()[0]) != 0:
+            raise L.MpreidError("rank_eval: positives workspace overflow after resize")
+    return res.first_hit, res.ap, res.num_rel
 
 
 def reduce_cmc_map(first_hit, ap, num_rel, max_rank: int, num_g: int, denominators: str = "valid"):

@@ -47,6 +47,48 @@ def _to_device(x, dev):
     return x.to(dev, non_blocking=True)
 
 
+class LabelSeq:
+    """The accumulated pids / camids.  The reference keeps Python lists of numpy scalars
+    (utils/metrics.py:107-108: ``self.pids.extend(np.asarray(pid))``), which costs milliseconds per
+    evaluation at MSMT17 size; this sequence stores the per-batch arrays and behaves like that list
+    (len, indexing, slicing, iteration, ==, np.asarray) without materialising it."""
+
+    def __init__(self):
+        self._chunks = []
+        self._flat = None
+
+    def extend(self, values):
+        self._chunks.append(np.asarray(values).reshape(-1))
+        self._flat = None
+
+    def append(self, value):
+        self.extend([value])
+
+    def array(self) -> np.ndarray:
+        if self._flat is None:
+            self._flat = np.concatenate(self._chunks) if self._chunks else np.zeros((0,), dtype=np.int64)
+        return self._flat
+
+    def __len__(self):
+        return int(sum(c.shape[0] for c in self._chunks))
+
+    def __getitem__(self, item):
+        return self.array()[item]
+
+    def __iter__(self):
+        return iter(self.array())
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.array()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __eq__(self, other):
+        return len(self) == len(other) and bool(np.all(self.array() == np.asarray(other)))
+
+    def __repr__(self):
+        return f"LabelSeq({self.array()!r})"
+
+
 class LazyDistmat:
     """ndarray-like handle on the device-resident [Q, G] distance matrix.
 
@@ -113,8 +155,8 @@ def _eval_device(dist_dev, q_pids, g_pids, q_camids, g_camids, max_rank, junk, d
     if num_g < max_rank:  # utils/metrics.py:36-38
         max_rank = num_g
         print("Note: number of gallery samples is quite small, got {}".format(num_g))
-    first_hit, ap, num_rel = E.rank_eval(dist_dev, q_pids, g_pids, q_camids, g_camids, junk)
-    return E.reduce_cmc_map(first_hit.cpu().numpy(), ap.cpu().numpy(), num_rel.cpu().numpy(), max_rank, num_g, denominators)
+    first_hit, ap, num_rel = E.rank_eval_host(dist_dev, q_pids, g_pids, q_camids, g_camids, junk)   # one D2H copy
+    return E.reduce_cmc_map(first_hit, ap, num_rel, max_rank, num_g, denominators)
 
 
 def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50, *, junk=None):
@@ -164,8 +206,8 @@ class R1_mAP_eval():
 
     def reset(self):
         self.feats = []
-        self.pids = []
-        self.camids = []
+        self.pids = LabelSeq()
+        self.camids = LabelSeq()
         self._events = []
 
     def update(self, output):  # called once for each batch
@@ -187,8 +229,8 @@ class R1_mAP_eval():
                 ev.record(cs)
             feats.append(t)
             self._events.append(ev)
-        self.pids.extend(np.asarray(pid))
-        self.camids.extend(np.asarray(camid))
+        self.pids.extend(pid)
+        self.camids.extend(camid)
 
     def _wait(self, lo, hi):
         cur = torch.cuda.current_stream()
