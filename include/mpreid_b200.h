@@ -106,6 +106,13 @@ MPREID_API int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
                        int metric, int precision,
                        float* out, int64_t ld_out, float* row_max, void* stream);
 
+/* All-pairs flavour (utils/reranking.py:36-41: the stacked features against themselves).  Only the
+ * tiles on or right of the diagonal are contracted; each of them also stores its transpose, so the
+ * matrix is exactly symmetric and the tensor-core work is halved.  row_max as above.             */
+MPREID_API int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, const float* x_aux, const float* x_scale,
+                                 int64_t N, int64_t K, int64_t ldk, int metric, int precision,
+                                 float* out, int64_t ld_out, float* row_max, void* stream);
+
 /* ---- ranking + CMC / AP ------------------------------------------------------------------------
  * Replaces eval_func (utils/metrics.py:28-88).  The Q x G argsort is never formed: for every query
  * the kernel takes the gallery entries with the query's pid (a hash-grouped label index), sorts

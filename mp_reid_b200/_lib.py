@@ -32,6 +32,7 @@ SIGNATURES = {
     "mpreid_device_info": (_i32, [_i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "mpreid_prep_rows": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "mpreid_dist_matrix": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
+    "mpreid_dist_matrix_symmetric": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
     "mpreid_rank_eval_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mpreid_rank_eval": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _sz, _i64, _p, _p]),
     "mpreid_row_topk": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),

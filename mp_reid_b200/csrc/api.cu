@@ -31,7 +31,7 @@ int launch_dist_simt(const float* q, const float* g, const float* q_aux, const f
                      int64_t K, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st);
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                    const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
-                   float* row_max, cudaStream_t st);
+                   float* row_max, int symmetric, cudaStream_t st);
 
 }  // namespace mpreid
 
@@ -68,7 +68,25 @@ extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
                  "dist_matrix: unknown precision %d", precision);
   MPREID_REQUIRE(precision == MPREID_BF16 || (qb && gb), "dist_matrix: the split modes need the lo planes");
   MPREID_REQUIRE(precision != MPREID_3XFP16 || (q_scale && g_scale), "dist_matrix: 3xFP16 needs the per-row scales");
-  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, st);
+  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, 0, st);
+}
+
+extern "C" int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, const float* x_aux, const float* x_scale,
+                                            int64_t N, int64_t K, int64_t ldk, int metric, int precision,
+                                            float* out, int64_t ld_out, float* row_max, void* stream) {
+  MPREID_REQUIRE(xa && out, "dist_matrix_symmetric: null operand");
+  MPREID_REQUIRE(N > 0 && K > 0 && ldk >= K && ld_out >= N && N < INT32_MAX, "dist_matrix_symmetric: bad shape N=%lld K=%lld", (long long)N,
+                 (long long)K);
+  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_SQRT_EUCLID, "dist_matrix_symmetric: unknown metric %d", metric);
+  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || x_aux, "dist_matrix_symmetric: metric %d needs x_aux", metric);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MPREID_FP32_SIMT)   // the validation kernel has no mirrored mode: plain all-pairs launch
+    return launch_dist_simt((const float*)xa, (const float*)xa, x_aux, x_aux, N, N, K, ldk, metric, out, ld_out, row_max, st);
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16,
+                 "dist_matrix_symmetric: unknown precision %d", precision);
+  MPREID_REQUIRE(precision == MPREID_BF16 || xb, "dist_matrix_symmetric: the split modes need the lo plane");
+  MPREID_REQUIRE(precision != MPREID_3XFP16 || x_scale, "dist_matrix_symmetric: 3xFP16 needs the per-row scales");
+  return launch_dist_tc(xa, xb, xa, xb, x_aux, x_aux, x_scale, x_scale, N, N, ldk, metric, precision, out, ld_out, row_max, 1, st);
 }
 
 extern "C" double mpreid_host_average_precision(const int32_t* ranks_host, int m, int64_t n) {

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
           const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
           float* __restrict__ out, int64_t ld_out,
-          float* __restrict__ row_max, int m_blocks, int n_blocks) {
+          float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric) {
   using C = Cfg<PREC>;
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
   constexpr int STAGE_BYTES = C::PLANES * (A_PLANE + B_PLANE);
@@ -222,6 +222,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
+        if (symmetric && t.n_blk < (t.m_blk >> 1)) continue;   // below the diagonal: filled by the mirror of another tile
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -240,9 +241,14 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     // ================================ MMA issuer ================================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (symmetric) {
+        const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
+        if (t.n_blk < (t.m_blk >> 1)) continue;
+      }
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      ++it;
       mbar_wait(tempty_bar(as), aph ^ 1u);   // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -284,10 +290,15 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 1024;
     float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
+      if (symmetric && t.n_blk < (t.m_blk >> 1)) continue;
+      // symmetric (all-pairs) mode: a tile strictly right of the diagonal block column also writes its
+      // transpose, which is exactly the set of tiles skipped above; diagonal tiles (n == m/2) do not
+      const bool mirror = symmetric && t.n_blk > (t.m_blk >> 1);
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      ++it;
       const int gm0 = t.m_blk * BM + quad * 32;
       const int gm = gm0 + lane;
       const bool row_ok = gm < Q;
@@ -356,6 +367,28 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
               }
             }
             __syncwarp();
+            if (mirror) {
+              // transpose: for a fixed column the 32 lanes hold 32 consecutive rows -> one 128-byte store
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (row_ok && gn0 + j < G) out[(int64_t)(gn0 + j) * ld_out + gm] = d[j];
+              if (row_max) {
+                // column maxima (the row maxima of the mirrored block): butterfly transpose-reduce, 31 shuffles
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (!row_ok) d[j] = -INFINITY;
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                  const bool upper = (lane & sft) != 0;
+#pragma unroll
+                  for (int tt = 0; tt < sft; ++tt) {
+                    const float send = upper ? d[tt] : d[tt + sft];
+                    const float keep = upper ? d[tt + sft] : d[tt];
+                    d[tt] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, sft));
+                  }
+                }
+                if (gn0 + lane < G && d[0] > -INFINITY) atomic_max_f32(&row_max[gn0 + lane], d[0]);
+              }
+            }
           }
         }
       }
@@ -403,7 +436,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, 
 
 template <int PREC>
 static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
-                  const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st) {
+                  const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max,
+                  int symmetric, cudaStream_t st) {
   using C = Cfg<PREC>;
   constexpr int kpb = ROW_BYTES / C::ELEM;
   MPREID_REQUIRE(ldk % kpb == 0, "dist_tc: operand planes must be padded to a multiple of %d elements (got %lld)", kpb, (long long)ldk);
@@ -437,7 +471,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
 #undef MPREID_PICK
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, (int)Q, (int)G, (int)(ldk / kpb), out, ld_out, row_max,
-                                    m_blocks, n_blocks);
+                                    m_blocks, n_blocks, symmetric);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }
@@ -446,7 +480,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
 
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                    const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
-                   float* row_max, cudaStream_t st) {
+                   float* row_max, int symmetric, cudaStream_t st) {
   int dev = 0, major = 0;
   MPREID_CUDA_CHECK(cudaGetDevice(&dev));
   MPREID_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -455,10 +489,10 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
     return MPREID_ERR_UNSUPPORTED;
   }
   if (precision == MPREID_3XTF32)
-    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
+    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
   if (precision == MPREID_3XFP16)
-    return tc::launch<MPREID_3XFP16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
-  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, st);
+    return tc::launch<MPREID_3XFP16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
+  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
 }
 
 }  // namespace mpreid

@@ -143,6 +143,36 @@ def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: s
     return out
 
 
+def dist_matrix_all_pairs(x: Prepared, precision: str | None = None, out: torch.Tensor | None = None,
+                          row_max: torch.Tensor | None = None, metric: str = "sqeuclid") -> torch.Tensor:
+    """utils/reranking.py:36-41: the stacked features against themselves; upper-triangle tiles + mirrored stores."""
+    require_cuda()
+    lib = L.load()
+    precision = (precision or default_precision()).lower()
+    prec, met = L.PRECISIONS[precision], L.METRICS[metric]
+    dev = x.sqnorm.device
+    if out is None:
+        out = alloc_dist(x.n, x.n, dev)
+    assert out.shape == (x.n, x.n) and out.stride(1) == 1 and out.dtype == torch.float32
+    aux = x.norm if met == L.ARCCOS else (None if met == L.ONE_MINUS_DOT else x.sqnorm)
+    if prec == L.FP32_SIMT:
+        a, b, K, ldk = x.xn, None, x.D, x.xn.stride(0)
+    elif prec == L.X3TF32:
+        a, b, K, ldk = x.hi, x.lo, x.Dp, x.Dp
+    elif prec == L.X3FP16:
+        a, b, K, ldk = x.hh, x.hl, x.Dp, x.Dp
+    else:
+        a, b, K, ldk = x.bf, None, x.Dp, x.Dp
+    if a is None:
+        raise ValueError(f"features were not prepared for precision '{precision}'")
+    if row_max is not None:
+        row_max.fill_(float("-inf"))
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_dist_matrix_symmetric(_ptr(a), _ptr(b), _ptr(aux), _ptr(x.hscale), x.n, K, ldk, met, prec,
+                                                 out.data_ptr(), out.stride(0), _ptr(row_max), _stream()), "dist_matrix_symmetric")
+    return out
+
+
 def _labels(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.int64, non_blocking=True)

@@ -24,7 +24,7 @@ def _all_pairs(prep: E.Prepared, precision=None, row_max: torch.Tensor | None = 
     n = prep.n
     ld = (n + 31) // 32 * 32
     buf = torch.empty((n, ld), dtype=torch.float32, device=prep.sqnorm.device)[:, :n]
-    return E.dist_matrix(prep, prep, "sqeuclid", precision, out=buf, row_max=row_max)
+    return E.dist_matrix_all_pairs(prep, precision, out=buf, row_max=row_max)
 
 
 def _rerank_device(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_value: float, precision=None,

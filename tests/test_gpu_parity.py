@@ -393,3 +393,28 @@ def test_row_sharded_rerank_equals_monolithic(golden_dir, world):
                                   N, nq, k1, k2, lam)
             got[q_lo:q_hi] = fin.cpu().numpy()
         assert np.array_equal(got, want), (world, k1, k2)
+
+
+# ------------------------------------------------------------------------------------ symmetric all-pairs GEMM
+@pytest.mark.parametrize("prec", ["3xfp16", "3xtf32", "bf16", "simt"])
+def test_all_pairs_symmetric_mode(prec):
+    torch.manual_seed(3)
+    for N, D in [(1, 16), (130, 100), (700, 256), (1300, 64)]:
+        x = torch.randn(N, D, device=DEV)
+        p = E.prep_rows(x, True, prec)
+        rm = torch.empty(N, device=DEV)
+        d = E.dist_matrix_all_pairs(p, prec, row_max=rm)
+        plain = E.dist_matrix(p, p, "sqeuclid", prec)
+        ii, jj = torch.arange(N, device=DEV)[:, None], torch.arange(N, device=DEV)[None, :]
+        mirrored = (jj // 256) > ((ii // 128) >> 1)                   # tiles strictly right of the diagonal block column
+        assert torch.equal(d[mirrored], d.t()[mirrored]), (prec, N)   # their transposes are stored, not recomputed
+        # inside the diagonal tiles (i,j) and (j,i) are separate accumulations of the split products: last-bit only
+        assert float((d - d.t()).abs().max()) <= (0.0 if prec in ("bf16",) else 2e-6), (prec, N)
+        iu = torch.triu(torch.ones(N, N, dtype=torch.bool, device=DEV))
+        tol = 1e-2 if prec == "bf16" else 2e-6
+        assert torch.all((d - plain).abs() <= tol), (prec, N, float((d - plain).abs().max()))
+        if prec != "simt":
+            # tiles on / right of the diagonal are the plain kernel's tiles
+            blk = (torch.arange(N, device=DEV)[None, :] // 256) >= (torch.arange(N, device=DEV)[:, None] // 256)
+            assert torch.equal(d[blk], plain[blk]), (prec, N)
+        assert torch.equal(rm, d.max(dim=1).values), (prec, N)
