@@ -305,20 +305,46 @@ def run_ours(args, data, workload):
                                      "frac": rank_gbs / pk["hbm"], "algorithmic": "4*Q*G bytes (distance matrix read once)",
                                      "peak_source": pk["source"]}}
 
-    # ---- re-rank ms (second half of the headline metric) on a shape that is cheap enough to repeat
+    # ---- re-rank ms (second half of the headline metric): prep + (Q+G)^2 distances + k-reciprocal re-ranking +
+    #      rank/CMC/mAP on the re-ranked matrix.  Fixed problem (strong scaling): with N ranks the rows of the
+    #      all-pairs matrix are sharded and the neighbour lists / V0 rows are all-gathered (distributed.rerank_sharded).
     rerank = None
     if args.rerank != "none":
+        from mp_reid_b200 import distributed as D
         rq, rg = (Q, G) if args.rerank == "full" else (min(Q, 3368), min(G, 15913))
         sub = torch.cat([feats_dev[:rq], feats_dev[Q:Q + rg]])
+        q_lo, q_hi = D.shard_bounds(rq, world, rank)
+        counts = [D.shard_bounds(rq, world, r)[1] - D.shard_bounds(rq, world, r)[0] for r in range(world)]
+
         def rr():
             p = E.prep_rows(sub, normalize=True, precision=prec, keep_xn=False)
-            dfin = _rerank_device(p, rq, args.k1, args.k2, 0.3, prec)
-            return E.rank_eval(dfin, lab["q_pid"][:rq], lab["g_pid"][:rg], lab["q_cam"][:rq], lab["g_cam"][:rg], junk)
-        rr_ms = kernel_ms(rr, 2)
-        fh, ap, nr = rr()
-        _, rr_map = E.reduce_cmc_map(fh.cpu().numpy(), ap.cpu().numpy(), nr.cpu().numpy(), 50, rg)
-        rerank = {"ms": rr_ms, "Q": rq, "G": rg, "k1": args.k1, "k2": args.k2, "lambda": 0.3, "mAP": float(rr_map),
-                  "includes": "prep + (Q+G)^2 distance + re-ranking + rank/AP kernels"}
+            if distributed:
+                dfin, _ = D.rerank_sharded(p, rq, args.k1, args.k2, 0.3, prec)
+            else:
+                dfin = _rerank_device(p, rq, args.k1, args.k2, 0.3, prec)
+            fh, ap, nr = E.rank_eval(dfin, lab["q_pid"][q_lo:q_hi], lab["g_pid"][:rg], lab["q_cam"][q_lo:q_hi], lab["g_cam"][:rg], junk)
+            if distributed:
+                return D.sharded_reduce(fh, ap, nr, counts, 50, rg)
+            return E.reduce_cmc_map(fh.cpu().numpy(), ap.cpu().numpy(), nr.cpu().numpy(), 50, rg)
+
+        rr(); torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        r0.record()
+        for _ in range(reps):
+            _, rr_map = rr()
+        r1.record(); torch.cuda.synchronize()
+        rr_ms = r0.elapsed_time(r1) / reps
+        if distributed:
+            t = torch.tensor([rr_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rr_ms = float(t.item())
+        rerank = {"ms": rr_ms, "unit": "ms", "n_gpus": world, "scaling": "strong", "Q": rq, "G": rg, "k1": args.k1, "k2": args.k2,
+                  "lambda": 0.3, "mAP": float(rr_map),
+                  "includes": "prep + (Q+G)^2 distance (upper-triangle tiles, mirrored) + k-reciprocal re-ranking + rank/CMC/mAP, "
+                              "features resident in HBM, result on the host"}
 
     if rank == 0:
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
@@ -364,7 +390,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MPREID_PRECISION", "3xfp16"))
     ap.add_argument("--metric", default="sqeuclid")
     ap.add_argument("--junk", default="none")
-    ap.add_argument("--rerank", default="market", choices=["none", "market", "full"])
+    ap.add_argument("--rerank", default="full", choices=["none", "market", "full"])
     ap.add_argument("--k1", type=int, default=20)
     ap.add_argument("--k2", type=int, default=6)
     ap.add_argument("--cpu-queries", type=int, default=1500, help="queries in the bounded CPU-baseline sample")

@@ -32,18 +32,30 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// One CTA per row (grid-stride).  Sweep 1: sum of squares + max |x| (only if normalising / scaling),
+// sweep 2 (the row is in L1/L2 by then): normalise, accumulate the squared norm of the OUTPUT row (the
+// reference takes the norms of the normalised features, utils/metrics.py:10-11) and emit the planes.
+// VEC: four consecutive columns per thread with 128-bit loads / stores (needs 16-byte aligned rows).
+template <bool VEC>
 __global__ void __launch_bounds__(kPrepThreads)
 k_prep_rows(const float* __restrict__ x, int64_t rows, int D, int64_t ld_x, int normalize,
             float* __restrict__ xn, int64_t ld_xn, float* __restrict__ sqnorm, float* __restrict__ norm,
             float* __restrict__ hi, float* __restrict__ lo, __nv_bfloat16* __restrict__ bf,
             __half* __restrict__ h_hi, __half* __restrict__ h_lo, float* __restrict__ h_scale_inv, int Dp) {
   __shared__ float sh[4];
+  constexpr int W = VEC ? 4 : 1;
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* xr = x + r * ld_x;
     float den = 1.0f, hscale = 1.0f;
     if (normalize || h_hi) {
       float s = 0.f, mx = 0.f;
-      for (int c = threadIdx.x; c < D; c += kPrepThreads) { float v = xr[c]; s = fmaf(v, v, s); mx = fmaxf(mx, fabsf(v)); }
+      for (int c = threadIdx.x * W; c < D; c += kPrepThreads * W) {
+        float v[W];
+        if (VEC) { const float4 t = *reinterpret_cast<const float4*>(xr + c); v[0] = t.x; v[W > 1 ? 1 : 0] = t.y; v[W > 2 ? 2 : 0] = t.z; v[W > 3 ? 3 : 0] = t.w; }
+        else v[0] = xr[c];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { s = fmaf(v[j], v[j], s); mx = fmaxf(mx, fabsf(v[j])); }
+      }
       if (normalize) {
         s = block_sum_128(s, sh);
         den = fmaxf(sqrtf(s), 1e-12f);  // F.normalize: x / max(||x||_2, eps)
@@ -58,25 +70,54 @@ k_prep_rows(const float* __restrict__ x, int64_t rows, int D, int64_t ld_x, int 
       }
     }
     float s2 = 0.f;
-    for (int c = threadIdx.x; c < Dp; c += kPrepThreads) {
-      float v = 0.f;
-      if (c < D) {
-        v = xr[c];
-        if (normalize) v = v / den;
-        s2 = fmaf(v, v, s2);
-        if (xn) xn[r * ld_xn + c] = v;
+    for (int c = threadIdx.x * W; c < Dp; c += kPrepThreads * W) {
+      float v[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = 0.f;
+      if (c < D) {   // D % 4 == 0 in the vector path, so a group is entirely inside or entirely padding
+        if (VEC) { const float4 t = *reinterpret_cast<const float4*>(xr + c); v[0] = t.x; v[W > 1 ? 1 : 0] = t.y; v[W > 2 ? 2 : 0] = t.z; v[W > 3 ? 3 : 0] = t.w; }
+        else v[0] = xr[c];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          if (normalize) v[j] = v[j] / den;
+          s2 = fmaf(v[j], v[j], s2);
+        }
+        if (xn) {
+          if (VEC) *reinterpret_cast<float4*>(xn + r * ld_xn + c) = make_float4(v[0], v[W > 1 ? 1 : 0], v[W > 2 ? 2 : 0], v[W > 3 ? 3 : 0]);
+          else xn[r * ld_xn + c] = v[0];
+        }
       }
+      const int64_t o = r * (int64_t)Dp + c;
       if (hi) {
-        const float h = to_tf32(v);
-        hi[r * (int64_t)Dp + c] = h;
-        lo[r * (int64_t)Dp + c] = to_tf32(v - h);
+        float h[W], l[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { h[j] = to_tf32(v[j]); l[j] = to_tf32(v[j] - h[j]); }
+        if (VEC) {
+          *reinterpret_cast<float4*>(hi + o) = make_float4(h[0], h[W > 1 ? 1 : 0], h[W > 2 ? 2 : 0], h[W > 3 ? 3 : 0]);
+          *reinterpret_cast<float4*>(lo + o) = make_float4(l[0], l[W > 1 ? 1 : 0], l[W > 2 ? 2 : 0], l[W > 3 ? 3 : 0]);
+        } else { hi[o] = h[0]; lo[o] = l[0]; }
       }
-      if (bf) bf[r * (int64_t)Dp + c] = __float2bfloat16_rn(v);
+      if (bf) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) bf[o + j] = __float2bfloat16_rn(v[j]);
+      }
       if (h_hi) {
-        const float xs = v * hscale;               // exact (power of two)
-        const __half h = __float2half_rn(xs);
-        h_hi[r * (int64_t)Dp + c] = h;
-        h_lo[r * (int64_t)Dp + c] = __float2half_rn(xs - __half2float(h));
+        __half hh[W], hl[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const float xs = v[j] * hscale;               // exact (power of two)
+          hh[j] = __float2half_rn(xs);
+          hl[j] = __float2half_rn(xs - __half2float(hh[j]));
+        }
+        if (VEC) {
+          uint2 ph, pl;
+          ph.x = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[W > 1 ? 1 : 0]) << 16);
+          ph.y = (uint32_t)__half_as_ushort(hh[W > 2 ? 2 : 0]) | ((uint32_t)__half_as_ushort(hh[W > 3 ? 3 : 0]) << 16);
+          pl.x = (uint32_t)__half_as_ushort(hl[0]) | ((uint32_t)__half_as_ushort(hl[W > 1 ? 1 : 0]) << 16);
+          pl.y = (uint32_t)__half_as_ushort(hl[W > 2 ? 2 : 0]) | ((uint32_t)__half_as_ushort(hl[W > 3 ? 3 : 0]) << 16);
+          *reinterpret_cast<uint2*>(h_hi + o) = ph;
+          *reinterpret_cast<uint2*>(h_lo + o) = pl;
+        } else { h_hi[o] = hh[0]; h_lo[o] = hl[0]; }
       }
     }
     s2 = block_sum_128(s2, sh);
@@ -106,8 +147,11 @@ extern "C" int mpreid_prep_rows(const float* x, int64_t rows, int64_t D, int64_t
   MPREID_REQUIRE(!(bf || h_hi) || Dp % 64 == 0, "prep_rows: 16-bit planes need Dp to be a multiple of 64");
   MPREID_REQUIRE(D < (1 << 30), "prep_rows: D too large");
   const int dp = planes ? (int)Dp : (int)D;
-  int64_t grid = rows < 148 * 16 ? rows : 148 * 16;
-  k_prep_rows<<<(unsigned)grid, kPrepThreads, 0, (cudaStream_t)stream>>>(
+  int64_t grid = rows < 148 * 32 ? rows : 148 * 32;
+  const bool vec = D % 4 == 0 && ld_x % 4 == 0 && ((uintptr_t)x & 15) == 0 && dp % 4 == 0 &&
+                   (!xn || (ld_xn % 4 == 0 && ((uintptr_t)xn & 15) == 0));
+  auto kern = vec ? k_prep_rows<true> : k_prep_rows<false>;
+  kern<<<(unsigned)grid, kPrepThreads, 0, (cudaStream_t)stream>>>(
       x, rows, (int)D, ld_x, normalize, xn, ld_xn, sqnorm, norm, hi, lo, (__nv_bfloat16*)bf,
       (__half*)h_hi, (__half*)h_lo, h_scale_inv, dp);
   MPREID_CUDA_CHECK(cudaGetLastError());
