@@ -179,6 +179,14 @@ MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* ro
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);
 
+/* ---- batch-hard mining (forward only) --------------------------------------------------------------
+ * loss/triplet_loss.py:50-103 on an [N, N] distance matrix (e.g. MPREID_SQRT_EUCLID of a batch against
+ * itself): dist_ap[i] = max over same-label j (the diagonal included), dist_an[i] = min over other-label
+ * j; p_inds / n_inds (optional) are the absolute column indices, first index on ties.  A row without
+ * other-label entries gets dist_an = +inf, n_inds = -1.                                              */
+MPREID_API int mpreid_hard_example_mining(const float* dist, int64_t ld_dist, int64_t N, const int64_t* labels,
+                               float* dist_ap, float* dist_an, int64_t* p_inds, int64_t* n_inds, void* stream);
+
 /* ---- host-side hooks (no GPU needed) -----------------------------------------------------------
  * The scalar arithmetic the kernels run is __host__ __device__ code; these two entry points run it
  * on the CPU so the CPU-only test-suite can check it bit-for-bit against numpy.

@@ -21,6 +21,7 @@
 // Tiles are visited band-major (16 m-blocks per band, m fastest) so the query band stays in L2 and
 // every gallery tile is fetched from HBM once per band.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "epilogue.cuh"
 
@@ -29,7 +30,6 @@ namespace tc {
 
 static constexpr int BM = 128;       // UMMA_M
 static constexpr int BN = 256;       // UMMA_N
-static constexpr int ROW_BYTES = 128;  // K bytes per smem row = one 128B swizzle atom
 static constexpr int THREADS = 192;
 static constexpr int TMEM_COLS = 512;
 static constexpr int BAND = 16;      // m-blocks per L2 band
@@ -43,6 +43,12 @@ template <> struct Cfg<MPREID_BF16> {
 };
 template <> struct Cfg<MPREID_3XFP16> {
   static constexpr int PLANES = 2, ELEM = 2, UMMA_K = 16, STAGES = 2, FMT = 0 /*F16*/;
+};
+
+// per-row-width pipeline shape: 64-byte rows halve the stage and double the depth
+template <int PREC, int ROWB> struct Pipe {
+  static constexpr int PLANES = Cfg<PREC>::PLANES, ELEM = Cfg<PREC>::ELEM, UMMA_K = Cfg<PREC>::UMMA_K, FMT = Cfg<PREC>::FMT;
+  static constexpr int STAGES = Cfg<PREC>::STAGES * (128 / ROWB);
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -138,12 +144,14 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major operand, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
 // bits: [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+// ROWB = 64 is the same with 64-byte rows / 64B swizzle (8-row groups 512 B apart, layout = 4).
+template <int ROWB>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)(((8 * ROWB) >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
   return d;
 }
 
@@ -165,17 +173,54 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int m_blocks, int n_b
   return t;
 }
 
+// Symmetric (all-pairs) mode visits only the tiles with n_blk >= m_blk/2 (on or right of the diagonal block
+// column), enumerated band by band in the same order as above so that the round-robin over CTAs stays balanced.
+__host__ __device__ __forceinline__ int sym_band_tiles(int b, int m_blocks, int n_blocks, int* h_out, int* jt_out) {
+  const int m0 = b * BAND;
+  const int h = (BAND < m_blocks - m0) ? BAND : (m_blocks - m0);
+  const int avail = n_blocks - (m0 >> 1);          // gallery blocks from the band's first diagonal block on
+  const int jf = (h - 1) / 2;                      // leading columns that hold fewer than h valid tiles: 2, 4, ...
+  const int jt = avail < jf ? (avail < 0 ? 0 : avail) : jf;
+  if (h_out) { *h_out = h; *jt_out = jt; }
+  const int flat = avail - jf;
+  return jt * (jt + 1) + (flat > 0 ? flat * h : 0);
+}
+__host__ __device__ __forceinline__ int sym_total_tiles(int m_blocks, int n_blocks) {
+  int t = 0;
+  for (int b = 0; b * BAND < m_blocks; ++b) t += sym_band_tiles(b, m_blocks, n_blocks, nullptr, nullptr);
+  return t;
+}
+__device__ __forceinline__ TileCoord sym_decode_tile(int tile, int m_blocks, int n_blocks) {
+  int b = 0, h = 0, jt = 0;
+  for (;; ++b) {
+    const int tb = sym_band_tiles(b, m_blocks, n_blocks, &h, &jt);
+    if (tile < tb) break;
+    tile -= tb;
+  }
+  const int m0 = b * BAND, n0 = m0 >> 1;
+  TileCoord t;
+  if (tile < jt * (jt + 1)) {
+    int j = 0;
+    while (tile >= 2 * j + 2) { tile -= 2 * j + 2; ++j; }
+    t.n_blk = n0 + j; t.m_blk = m0 + tile;
+  } else {
+    tile -= jt * (jt + 1);
+    t.n_blk = n0 + jt + tile / h; t.m_blk = m0 + tile % h;
+  }
+  return t;
+}
+
 struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int PREC, int METRIC, bool VEC>
+template <int PREC, int ROW_BYTES, int METRIC, bool VEC>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
           const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
           float* __restrict__ out, int64_t ld_out,
           float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric) {
-  using C = Cfg<PREC>;
+  using C = Pipe<PREC, ROW_BYTES>;
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
   constexpr int STAGE_BYTES = C::PLANES * (A_PLANE + B_PLANE);
   constexpr int K_PER_BLOCK = ROW_BYTES / C::ELEM;       // elements of K per stage
@@ -195,7 +240,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int total_tiles = m_blocks * n_blocks;
+  const int total_tiles = symmetric ? sym_total_tiles(m_blocks, n_blocks) : m_blocks * n_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.b_hi);
@@ -221,8 +266,8 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
-        if (symmetric && t.n_blk < (t.m_blk >> 1)) continue;   // below the diagonal: filled by the mirror of another tile
+        // symmetric mode: tiles below the diagonal block column are never visited, the mirrors fill them
+        const TileCoord t = symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -242,10 +287,6 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      if (symmetric) {
-        const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
-        if (t.n_blk < (t.m_blk >> 1)) continue;
-      }
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       ++it;
@@ -258,13 +299,13 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
         if (lane == 0) {
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint32_t sb = sa + C::PLANES * A_PLANE;
-          const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sb);
+          const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sa), b_hi = make_smem_desc<ROW_BYTES>(sb);
 #pragma unroll
           for (int k = 0; k < K_STEPS; ++k) {
             const uint64_t koff = (uint64_t)((k * C::UMMA_K * C::ELEM) >> 4);  // +32 B per k-step inside the atom
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             if (C::PLANES == 2) {
-              const uint64_t a_lo = make_smem_desc(sa + A_PLANE), b_lo = make_smem_desc(sb + B_PLANE);
+              const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sa + A_PLANE), b_lo = make_smem_desc<ROW_BYTES>(sb + B_PLANE);
               umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
               umma<PREC>(tmem_d, a_hi + koff, b_lo + koff, IDESC, 1u);
               umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
@@ -291,8 +332,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(tile, m_blocks, n_blocks);
-      if (symmetric && t.n_blk < (t.m_blk >> 1)) continue;
+      const TileCoord t = symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
       // symmetric (all-pairs) mode: a tile strictly right of the diagonal block column also writes its
       // transpose, which is exactly the set of tiles skipped above; diagonal tiles (n == m/2) do not
       const bool mirror = symmetric && t.n_blk > (t.m_blk >> 1);
@@ -420,21 +460,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, int elem, int box_rows) {
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, int elem, int box_rows, int rowb) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return MPREID_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)ldk, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ldk * elem};
-  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(rowb / elem), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MPREID_ERR_CUDA; }
   return MPREID_OK;
 }
 
-template <int PREC>
+template <int PREC, int ROW_BYTES>
 static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                   const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max,
                   int symmetric, cudaStream_t st) {
@@ -445,23 +485,23 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  if ((rc = make_map(&maps.a_hi, qa, Q, ldk, C::ELEM, BM)) != MPREID_OK) return rc;
-  if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN)) != MPREID_OK) return rc;
+  if ((rc = make_map(&maps.a_hi, qa, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
+  if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
   if (C::PLANES == 2) {
-    if ((rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM)) != MPREID_OK) return rc;
-    if ((rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN)) != MPREID_OK) return rc;
+    if ((rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
+    if ((rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
   }
   const int m_blocks = (int)ceil_div(Q, BM), n_blocks = (int)ceil_div(G, BN);
-  const int64_t total = (int64_t)m_blocks * n_blocks;
-  MPREID_REQUIRE(total < INT32_MAX, "dist_tc: too many tiles");
+  MPREID_REQUIRE((int64_t)m_blocks * n_blocks < INT32_MAX, "dist_tc: too many tiles");
+  const int64_t total = symmetric ? sym_total_tiles(m_blocks, n_blocks) : (int64_t)m_blocks * n_blocks;
   const int sms = sm_count_of_current_device();
   const int grid = (int)(total < sms ? total : sms);
   constexpr int STAGE_BYTES = C::PLANES * (BM + BN) * ROW_BYTES;
-  const int smem = C::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
+  const int smem = C::STAGES * (128 / ROW_BYTES) * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
   const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  using KernT = decltype(&k_dist_tc<PREC, MPREID_SQEUCLID, true>);   // no casts: a signature mismatch must not compile
+  using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true>);   // no casts: a signature mismatch must not compile
   KernT kern = nullptr;
-#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, M, true> : &k_dist_tc<PREC, M, false>
+#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, M, true> : &k_dist_tc<PREC, ROW_BYTES, M, false>
   switch (metric) {
     case MPREID_SQEUCLID: MPREID_PICK(MPREID_SQEUCLID); break;
     case MPREID_ARCCOS: MPREID_PICK(MPREID_ARCCOS); break;
@@ -488,11 +528,19 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
     set_error("dist_tc: the tcgen05 kernels need an sm_100 GPU (found compute capability %d.x)", major);
     return MPREID_ERR_UNSUPPORTED;
   }
+  // pipeline shape: 128-byte rows x 2 stages, or (MPREID_GEMM_ROWB=64) 64-byte rows x 4 stages for the split modes
+  static int rowb = 0;
+  if (rowb == 0) {
+    const char* e = getenv("MPREID_GEMM_ROWB");
+    rowb = (e && atoi(e) == 64) ? 64 : 128;
+  }
+#define MPREID_ARGS qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st
   if (precision == MPREID_3XTF32)
-    return tc::launch<MPREID_3XTF32>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
+    return rowb == 64 ? tc::launch<MPREID_3XTF32, 64>(MPREID_ARGS) : tc::launch<MPREID_3XTF32, 128>(MPREID_ARGS);
   if (precision == MPREID_3XFP16)
-    return tc::launch<MPREID_3XFP16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
-  return tc::launch<MPREID_BF16>(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st);
+    return rowb == 64 ? tc::launch<MPREID_3XFP16, 64>(MPREID_ARGS) : tc::launch<MPREID_3XFP16, 128>(MPREID_ARGS);
+  return tc::launch<MPREID_BF16, 128>(MPREID_ARGS);
+#undef MPREID_ARGS
 }
 
 }  // namespace mpreid

@@ -419,34 +419,47 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
           st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
         }
         __syncthreads();
-        int32_t pre_row = 0; uint16_t pre_val = 0;
-        if (tid < st.n[0]) { pre_row = csc_row[st.b[0] + tid]; pre_val = csc_val[st.b[0] + tid]; }
-        for (int e = 0; e < nb; ++e) {
-          const int n = st.n[e];
-          const int64_t b = st.b[e];
-          const __half vik = __ushort_as_half(st.v[e]);
-          const int32_t cur_row = pre_row; const uint16_t cur_val = pre_val;
-          if (e + 1 < nb && tid < st.n[e + 1]) {             // in flight while step e is applied
-            pre_row = csc_row[st.b[e + 1] + tid];
-            pre_val = csc_val[st.b[e + 1] + tid];
-          }
-          if (tid < n) {
-            const int c = cur_row - Q - t0;
-            if (c >= 0 && c < tn) {
-              const __half vg = __ushort_as_half(cur_val);
-              const __half mn = __hlt(vg, vik) ? vg : vik;
-              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+        // every thread keeps its list entry of the next kJacAhead steps in flight (one L2 round trip per step
+        // would otherwise bound the loop)
+        constexpr int kJacAhead = 4;
+        int32_t pre_row[kJacAhead]; uint16_t pre_val[kJacAhead];
+#pragma unroll
+        for (int u = 0; u < kJacAhead; ++u) {
+          pre_row[u] = 0; pre_val[u] = 0;
+          if (u < nb && tid < st.n[u]) { pre_row[u] = csc_row[st.b[u] + tid]; pre_val[u] = csc_val[st.b[u] + tid]; }
+        }
+        for (int e0 = 0; e0 < nb; e0 += kJacAhead) {
+#pragma unroll
+          for (int u = 0; u < kJacAhead; ++u) {
+            const int e = e0 + u;
+            if (e < nb) {   // block-uniform
+              const int n = st.n[e];
+              const int64_t b = st.b[e];
+              const __half vik = __ushort_as_half(st.v[e]);
+              const int32_t cur_row = pre_row[u]; const uint16_t cur_val = pre_val[u];
+              if (e + kJacAhead < nb && tid < st.n[e + kJacAhead]) {
+                pre_row[u] = csc_row[st.b[e + kJacAhead] + tid];
+                pre_val[u] = csc_val[st.b[e + kJacAhead] + tid];
+              }
+              if (tid < n) {
+                const int c = cur_row - Q - t0;
+                if (c >= 0 && c < tn) {
+                  const __half vg = __ushort_as_half(cur_val);
+                  const __half mn = __hlt(vg, vik) ? vg : vik;
+                  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+                }
+              }
+              for (int uu = tid + kJacThreads; uu < n; uu += kJacThreads) {   // lists longer than the CTA (rare)
+                const int c = csc_row[b + uu] - Q - t0;
+                if (c >= 0 && c < tn) {
+                  const __half vg = __ushort_as_half(csc_val[b + uu]);
+                  const __half mn = __hlt(vg, vik) ? vg : vik;
+                  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+                }
+              }
+              __syncthreads();
             }
           }
-          for (int u = tid + kJacThreads; u < n; u += kJacThreads) {   // lists longer than the CTA (rare)
-            const int c = csc_row[b + u] - Q - t0;
-            if (c >= 0 && c < tn) {
-              const __half vg = __ushort_as_half(csc_val[b + u]);
-              const __half mn = __hlt(vg, vik) ? vg : vik;
-              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
-            }
-          }
-          __syncthreads();
         }
       }
       __syncthreads();

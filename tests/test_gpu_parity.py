@@ -478,3 +478,23 @@ def test_nan_and_inf_distances_rank_like_numpy():
     assert np.array_equal(fh.cpu().numpy(), want["first_hit"]) and np.array_equal(ap.cpu().numpy(), want["ap"])
     idx = E.row_topk(dev(d), 64).cpu().numpy()
     assert np.array_equal(idx, np.argsort(d, axis=1, kind="stable")[:, :64])
+
+
+# ------------------------------------------------------------------------------------ batch-hard mining
+def test_triplet_distance_and_hard_mining_forward():
+    from mp_reid_b200 import triplet
+    torch.manual_seed(5)
+    for (P, K, D) in [(16, 4, 1280), (8, 8, 768), (5, 3, 33)]:
+        x = torch.randn(P * K, D, device=DEV)
+        labels = torch.arange(P, device=DEV).repeat_interleave(K)[torch.randperm(P * K, device=DEV)]
+        d = triplet.euclidean_dist(x, x)
+        ref = orc.sqrt_euclidean(x.cpu().numpy(), x.cpu().numpy())
+        off = ~np.eye(P * K, dtype=bool)      # the diagonal is sqrt(cancellation noise), ill-conditioned by construction
+        assert np.abs(d.cpu().numpy() - ref)[off].max() <= 1e-3 * ref[off].max()
+        ap, an, pi, ni = triplet.hard_example_mining(d, labels, return_inds=True)
+        dm, lab = d.cpu(), labels.cpu()
+        is_pos = lab[None, :] == lab[:, None]
+        want_ap, want_pi = torch.where(is_pos, dm, torch.full_like(dm, -float("inf"))).max(1)
+        want_an, want_ni = torch.where(~is_pos, dm, torch.full_like(dm, float("inf"))).min(1)
+        assert torch.equal(ap.cpu(), want_ap) and torch.equal(an.cpu(), want_an)
+        assert torch.equal(dm[torch.arange(P * K), pi.cpu()], want_ap) and torch.equal(dm[torch.arange(P * K), ni.cpu()], want_an)
