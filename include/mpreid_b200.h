@@ -53,8 +53,11 @@ enum mpreid_precision {
   MPREID_FP32_SIMT = 0, /* plain fp32 FFMA tiles (validation / tiny shapes)                        */
   MPREID_3XTF32 = 1,    /* tcgen05 kind::tf32, error-compensated hi/lo split: fp32-accurate        */
   MPREID_BF16 = 2,      /* tcgen05 kind::f16 on bf16-rounded operands, fp32 accumulate             */
-  MPREID_3XFP16 = 3     /* tcgen05 kind::f16 on a per-row power-of-two scaled fp16 hi/lo split:
+  MPREID_3XFP16 = 3,    /* tcgen05 kind::f16 on a per-row power-of-two scaled fp16 hi/lo split:
                            fp32-accurate like 3xTF32 at twice the MMA rate                          */
+  MPREID_2XFP16 = 4     /* same planes, but the gallery side contributes only its hi plane (drops hi*lo):
+                           two MMAs per k-step, error ~2^-12 per product; a stated fast mode, same
+                           operands as MPREID_3XFP16 (gb may be NULL)                                */
 };
 
 enum mpreid_junk {

@@ -16,12 +16,12 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "mpreid_b200.h")
 
 # enums of include/mpreid_b200.h
 SQEUCLID, ARCCOS, ONE_MINUS_DOT, SQRT_EUCLID = 0, 1, 2, 3
-FP32_SIMT, X3TF32, BF16, X3FP16 = 0, 1, 2, 3
+FP32_SIMT, X3TF32, BF16, X3FP16, X2FP16 = 0, 1, 2, 3, 4
 JUNK_NONE, JUNK_PID_CAM = 0, 1
 
 METRICS = {"sqeuclid": SQEUCLID, "euclidean": SQEUCLID, "arccos": ARCCOS, "cosine": ARCCOS,
            "one_minus_dot": ONE_MINUS_DOT, "1-cos": ONE_MINUS_DOT, "sqrt_euclid": SQRT_EUCLID}
-PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "3xtf32": X3TF32, "bf16": BF16, "3xfp16": X3FP16, "fp32": X3FP16}
+PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "3xtf32": X3TF32, "bf16": BF16, "3xfp16": X3FP16, "fp32": X3FP16, "2xfp16": X2FP16}
 JUNKS = {"none": JUNK_NONE, "pid_cam": JUNK_PID_CAM}
 
 _p, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t

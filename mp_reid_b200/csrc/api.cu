@@ -64,10 +64,11 @@ extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MPREID_FP32_SIMT)
     return launch_dist_simt((const float*)qa, (const float*)ga, q_aux, g_aux, Q, G, K, ldk, metric, out, ld_out, row_max, st);
-  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16,
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16 || precision == MPREID_2XFP16,
                  "dist_matrix: unknown precision %d", precision);
-  MPREID_REQUIRE(precision == MPREID_BF16 || (qb && gb), "dist_matrix: the split modes need the lo planes");
-  MPREID_REQUIRE(precision != MPREID_3XFP16 || (q_scale && g_scale), "dist_matrix: 3xFP16 needs the per-row scales");
+  MPREID_REQUIRE(precision == MPREID_BF16 || (qb && (gb || precision == MPREID_2XFP16)), "dist_matrix: the split modes need the lo planes");
+  MPREID_REQUIRE((precision != MPREID_3XFP16 && precision != MPREID_2XFP16) || (q_scale && g_scale),
+                 "dist_matrix: the FP16 split modes need the per-row scales");
   return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, 0, st);
 }
 
@@ -82,10 +83,11 @@ extern "C" int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MPREID_FP32_SIMT)   // the validation kernel has no mirrored mode: plain all-pairs launch
     return launch_dist_simt((const float*)xa, (const float*)xa, x_aux, x_aux, N, N, K, ldk, metric, out, ld_out, row_max, st);
-  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16,
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16 || precision == MPREID_2XFP16,
                  "dist_matrix_symmetric: unknown precision %d", precision);
   MPREID_REQUIRE(precision == MPREID_BF16 || xb, "dist_matrix_symmetric: the split modes need the lo plane");
-  MPREID_REQUIRE(precision != MPREID_3XFP16 || x_scale, "dist_matrix_symmetric: 3xFP16 needs the per-row scales");
+  MPREID_REQUIRE((precision != MPREID_3XFP16 && precision != MPREID_2XFP16) || x_scale,
+                 "dist_matrix_symmetric: the FP16 split modes need the per-row scales");
   return launch_dist_tc(xa, xb, xa, xb, x_aux, x_aux, x_scale, x_scale, N, N, ldk, metric, precision, out, ld_out, row_max, 1, st);
 }
 

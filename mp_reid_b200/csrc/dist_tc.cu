@@ -44,10 +44,18 @@ template <> struct Cfg<MPREID_BF16> {
 template <> struct Cfg<MPREID_3XFP16> {
   static constexpr int PLANES = 2, ELEM = 2, UMMA_K = 16, STAGES = 2, FMT = 0 /*F16*/;
 };
+// 2xFP16: the query side keeps the hi/lo split, the gallery side only its hi plane (11 bits): drops the
+// hi*lo term -> two MMAs per k-step, 64 KB stages x 3.  Error ~2^-12 per product: a stated fast mode.
+template <> struct Cfg<MPREID_2XFP16> {
+  static constexpr int PLANES = 2, ELEM = 2, UMMA_K = 16, STAGES = 3, FMT = 0 /*F16*/;
+};
+template <int PREC> struct PlanesB { static constexpr int value = Cfg<PREC>::PLANES; };
+template <> struct PlanesB<MPREID_2XFP16> { static constexpr int value = 1; };
 
 // per-row-width pipeline shape: 64-byte rows halve the stage and double the depth
 template <int PREC, int ROWB> struct Pipe {
-  static constexpr int PLANES = Cfg<PREC>::PLANES, ELEM = Cfg<PREC>::ELEM, UMMA_K = Cfg<PREC>::UMMA_K, FMT = Cfg<PREC>::FMT;
+  static constexpr int PLANES = Cfg<PREC>::PLANES, PLANES_B = PlanesB<PREC>::value;   // operand planes: query side, gallery side
+  static constexpr int ELEM = Cfg<PREC>::ELEM, UMMA_K = Cfg<PREC>::UMMA_K, FMT = Cfg<PREC>::FMT;
   static constexpr int STAGES = Cfg<PREC>::STAGES * (128 / ROWB);
 };
 
@@ -222,10 +230,11 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
           float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric) {
   using C = Pipe<PREC, ROW_BYTES>;
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
-  constexpr int STAGE_BYTES = C::PLANES * (A_PLANE + B_PLANE);
+  constexpr int STAGE_BYTES = C::PLANES * A_PLANE + C::PLANES_B * B_PLANE;
   constexpr int K_PER_BLOCK = ROW_BYTES / C::ELEM;       // elements of K per stage
   constexpr int K_STEPS = K_PER_BLOCK / C::UMMA_K;       // 4
   constexpr uint32_t IDESC = make_idesc(C::FMT, BM, BN);
+  constexpr bool kScaled = PREC == MPREID_3XFP16 || PREC == MPREID_2XFP16;   // operands carry per-row 2^s scales
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-B aligned tiles
@@ -244,7 +253,8 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.b_hi);
-    if (C::PLANES == 2) { prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_lo); }
+    if (C::PLANES == 2) prefetch_tmap(&maps.a_lo);
+    if (C::PLANES_B == 2) prefetch_tmap(&maps.b_lo);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -277,7 +287,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
           if (C::PLANES == 2) tma_load_2d(sa + A_PLANE, &maps.a_lo, full_bar(stage), kc, t.m_blk * BM);
           const uint32_t sb = sa + C::PLANES * A_PLANE;
           tma_load_2d(sb, &maps.b_hi, full_bar(stage), kc, t.n_blk * BN);
-          if (C::PLANES == 2) tma_load_2d(sb + B_PLANE, &maps.b_lo, full_bar(stage), kc, t.n_blk * BN);
+          if (C::PLANES_B == 2) tma_load_2d(sb + B_PLANE, &maps.b_lo, full_bar(stage), kc, t.n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -304,10 +314,14 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
           for (int k = 0; k < K_STEPS; ++k) {
             const uint64_t koff = (uint64_t)((k * C::UMMA_K * C::ELEM) >> 4);  // +32 B per k-step inside the atom
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (C::PLANES == 2) {
+            if (C::PLANES == 2 && C::PLANES_B == 2) {
               const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sa + A_PLANE), b_lo = make_smem_desc<ROW_BYTES>(sb + B_PLANE);
               umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
               umma<PREC>(tmem_d, a_hi + koff, b_lo + koff, IDESC, 1u);
+              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
+            } else if (C::PLANES == 2) {
+              const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sa + A_PLANE);
+              umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
               umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
             } else {
               umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, acc);
@@ -343,7 +357,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       const int gm = gm0 + lane;
       const bool row_ok = gm < Q;
       const float qa = (row_ok && q_aux) ? q_aux[gm] : 0.f;
-      const float qs = (PREC == MPREID_3XFP16 && row_ok) ? q_scale[gm] : 1.f;
+      const float qs = (kScaled && row_ok) ? q_scale[gm] : 1.f;
       float rmax = -INFINITY;
       float2* gvec = gvec_all + as * BN;
 #pragma unroll
@@ -352,7 +366,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
         float2 v = make_float2(1.f, 1.f);
         if (gn < G) {
           if (g_aux) v.x = __ldg(g_aux + gn);
-          if (PREC == MPREID_3XFP16) v.y = __ldg(g_scale + gn);
+          if (kScaled) v.y = __ldg(g_scale + gn);
         }
         gvec[c] = v;
       }
@@ -378,7 +392,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
             for (int j = 0; j < 32; ++j) {
               const float2 gv = gvec[cc + j];                       // broadcast read
               float dot = __uint_as_float(acc[half * 32 + j]);
-              if (PREC == MPREID_3XFP16) dot = dot * qs * gv.y;     // undo the 2^s row scales (exact)
+              if (kScaled) dot = dot * qs * gv.y;     // undo the 2^s row scales (exact)
               d[j] = finish_distance<METRIC>(dot, qa, gv.x);
               if (gn0 + j < G) rmax = fmaxf(rmax, d[j]);
             }
@@ -487,16 +501,14 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   int rc;
   if ((rc = make_map(&maps.a_hi, qa, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
   if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
-  if (C::PLANES == 2) {
-    if ((rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
-    if ((rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
-  }
+  if (C::PLANES == 2 && (rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
+  if (PlanesB<PREC>::value == 2 && (rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
   const int m_blocks = (int)ceil_div(Q, BM), n_blocks = (int)ceil_div(G, BN);
   MPREID_REQUIRE((int64_t)m_blocks * n_blocks < INT32_MAX, "dist_tc: too many tiles");
   const int64_t total = symmetric ? sym_total_tiles(m_blocks, n_blocks) : (int64_t)m_blocks * n_blocks;
   const int sms = sm_count_of_current_device();
   const int grid = (int)(total < sms ? total : sms);
-  constexpr int STAGE_BYTES = C::PLANES * (BM + BN) * ROW_BYTES;
+  constexpr int STAGE_BYTES = (C::PLANES * BM + PlanesB<PREC>::value * BN) * ROW_BYTES;
   const int smem = C::STAGES * (128 / ROW_BYTES) * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
   const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
   using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true>);   // no casts: a signature mismatch must not compile
@@ -539,6 +551,7 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
     return rowb == 64 ? tc::launch<MPREID_3XTF32, 64>(MPREID_ARGS) : tc::launch<MPREID_3XTF32, 128>(MPREID_ARGS);
   if (precision == MPREID_3XFP16)
     return rowb == 64 ? tc::launch<MPREID_3XFP16, 64>(MPREID_ARGS) : tc::launch<MPREID_3XFP16, 128>(MPREID_ARGS);
+  if (precision == MPREID_2XFP16) return tc::launch<MPREID_2XFP16, 128>(MPREID_ARGS);
   return tc::launch<MPREID_BF16, 128>(MPREID_ARGS);
 #undef MPREID_ARGS
 }

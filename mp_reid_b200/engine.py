@@ -76,14 +76,14 @@ def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, ke
         x = x.contiguous()
     n, D = x.shape
     dev = x.device
-    pad = 64 if prec in (L.BF16, L.X3FP16) else 32
+    pad = 64 if prec in (L.BF16, L.X3FP16, L.X2FP16) else 32
     Dp = (D + pad - 1) // pad * pad
     need_xn = keep_xn or prec == L.FP32_SIMT
     xn = torch.empty((n, D), dtype=torch.float32, device=dev) if need_xn else None
     sqnorm = torch.empty((n,), dtype=torch.float32, device=dev)
     norm = torch.empty((n,), dtype=torch.float32, device=dev)
     hi = lo = bf = hh = hl = hscale = None
-    if prec == L.X3FP16:
+    if prec in (L.X3FP16, L.X2FP16):
         hh = torch.empty((n, Dp), dtype=torch.float16, device=dev)
         hl = torch.empty((n, Dp), dtype=torch.float16, device=dev)
         hscale = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -128,7 +128,7 @@ def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: s
         a, b, c, d, K, ldk = q.xn, None, g.xn, None, q.D, q.xn.stride(0)
     elif prec == L.X3TF32:
         a, b, c, d, K, ldk = q.hi, q.lo, g.hi, g.lo, q.Dp, q.Dp
-    elif prec == L.X3FP16:
+    elif prec in (L.X3FP16, L.X2FP16):
         a, b, c, d, K, ldk = q.hh, q.hl, g.hh, g.hl, q.Dp, q.Dp
     else:
         a, b, c, d, K, ldk = q.bf, None, g.bf, None, q.Dp, q.Dp
@@ -159,7 +159,7 @@ def dist_matrix_all_pairs(x: Prepared, precision: str | None = None, out: torch.
         a, b, K, ldk = x.xn, None, x.D, x.xn.stride(0)
     elif prec == L.X3TF32:
         a, b, K, ldk = x.hi, x.lo, x.Dp, x.Dp
-    elif prec == L.X3FP16:
+    elif prec in (L.X3FP16, L.X2FP16):
         a, b, K, ldk = x.hh, x.hl, x.Dp, x.Dp
     else:
         a, b, K, ldk = x.bf, None, x.Dp, x.Dp

@@ -19,6 +19,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_shape(a.workload)
 nq, G = qf.shape[0], gf.shape[0]

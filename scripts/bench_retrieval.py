@@ -17,6 +17,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 s = synth.SHAPES["retrieval"]
 Q, G = int(s.Q * a.scale), int(s.G * a.scale)
