@@ -482,11 +482,7 @@ extern "C" int mpreid_rank_eval(const float* dist, int64_t ld_dist, int64_t Q, i
   int ctas_per_sm = 4;
   int grid = (int)((Q < (int64_t)sms * ctas_per_sm) ? Q : (int64_t)sms * ctas_per_sm);
   const int rank_smem = (int)sizeof(RankSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_rank_count, cudaFuncAttributeMaxDynamicSharedMemorySize, rank_smem));
-    attr_set = true;
-  }
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_rank_count, cudaFuncAttributeMaxDynamicSharedMemorySize, rank_smem));  // per device, cheap
   k_rank_count<<<grid, kRankThreads, rank_smem, st>>>(dist, ld_dist, (int)Q, (int)G, q_cam, g_cam, junk_mode != MPREID_JUNK_NONE,
                                               w.list, w.q_start, w.q_cnt, w.q_off, status, w.pos_tmp, w.pos_rank,
                                               first_hit, num_rel, w.row_len);

@@ -367,21 +367,35 @@ __global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, cons
 
 // ----------------------------------------------------------------------------------- Jaccard + blend
 static constexpr int kJacThreads = 512;
-static constexpr int kJacBlock = 256;      // V entries of the query row staged per round
-static constexpr int kJacMaxTile = 53248;  // fp16 accumulator entries per CTA: two CTAs per SM
+static constexpr int kJacWarps = kJacThreads / 32;
+static constexpr int kJacSteps = 64;       // V entries of the query row staged per round
+static constexpr int kJacListCap = 3072;   // inverted-list entries staged per round (24 KB)
+static constexpr int kJacMaxTile = 41600;  // fp16 accumulator entries per CTA (81 KB): two CTAs per SM (MSMT17 gallery = 2 tiles)
 
 struct JacStage {
-  int32_t n[kJacBlock];       // inverted-list length of column k_e
-  int64_t b[kJacBlock];       // its start in the CSC arrays
-  uint16_t v[kJacBlock];      // V[i, k_e]
+  int64_t b[kJacSteps];        // start of the inverted list of column k_e in the CSC arrays
+  int32_t n[kJacSteps];        // its length
+  int32_t pre[kJacSteps + 1];  // prefix of the lengths inside the round
+  uint16_t v[kJacSteps];       // V[i, k_e]
+  int32_t fit;                 // steps of this round whose lists fit the staging buffer (0: the first list alone is too long)
+  int32_t pad;
+  int32_t own_cnt[kJacThreads];      // staged entries per owner thread (owner = g mod 512)
+  int32_t own_off[kJacThreads + 1];  // their segment in ent[]
+  int32_t scan[33];
 };
 
-// One CTA per query row.  For every non-zero column k of V[i] (ascending: the reference's accumulation
-// order, :88-92) the gallery rows of the inverted list of k get  acc[g] = fp16(acc[g] + min(V[i,k], V[g,k])).
-// A list touches every g at most once, so a step needs no atomics, only a barrier before the next k.
-// The dependent global loads (V row -> list offsets -> list entries) are taken off the critical path:
-// the row's (k, offset, length) triples are staged in shared memory 256 at a time and every thread
-// fetches its list entry of step e+1 while step e is applied.
+__device__ __forceinline__ void jac_apply(__half* acc, int c, uint16_t vg_bits, __half vik) {
+  const __half vg = __ushort_as_half(vg_bits);
+  const __half mn = __hlt(vg, vik) ? vg : vik;
+  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));     // fp16 accumulator, one rounding per add (:87-91)
+}
+
+// One CTA per query row.  For every non-zero column k of V[i], in ascending k (the reference's accumulation
+// order, :88-92), the gallery rows g of the inverted list of k get  acc[g] = fp16(acc[g] + min(V[i,k], V[g,k])).
+// Only the order per g matters, so every accumulator entry gets an OWNER thread (g mod 512).  Rounds: the
+// offsets of up to 64 steps are staged, their list entries (<= 3072, all loads in flight at once) are bucketed
+// by owner in shared memory, and every thread applies its own few entries in step order -- no barrier per
+// step and no atomics on the accumulator.
 __global__ void __launch_bounds__(kJacThreads)
 k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ q_ids, int Qs, int N, int Q, float lambda_value,
           const float* __restrict__ rowmax,
@@ -390,8 +404,9 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
           float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
-  __half* acc = reinterpret_cast<__half*>(smem_raw + sizeof(JacStage));  // [tile_cols] fp16 accumulator (temp_min, :87)
-  const int tid = threadIdx.x;
+  uint64_t* ent = reinterpret_cast<uint64_t*>(smem_raw + sizeof(JacStage));                         // [kJacListCap] row | val << 32
+  __half* acc = reinterpret_cast<__half*>(smem_raw + ((sizeof(JacStage) + kJacListCap * 8 + 15) & ~size_t(15)));   // [tile_cols] temp_min (:87)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
   const __half h_one = __float2half_rn(1.f), h_two = __float2half_rn(2.f);
@@ -408,8 +423,9 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
         const int n4 = (tn + 7) >> 3;
         for (int c = tid; c < n4; c += kJacThreads) a4[c] = make_uint4(0u, 0u, 0u, 0u);
       }
-      for (int e0 = 0; e0 < len; e0 += kJacBlock) {
-        const int nb = min(kJacBlock, len - e0);
+      int e0 = 0;
+      while (e0 < len) {
+        const int nb = min(kJacSteps, len - e0);
         __syncthreads();   // previous round fully applied (and the zero fill visible) before the stage is rewritten
         if (tid < nb) {
           const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
@@ -419,67 +435,106 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
           st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
         }
         __syncthreads();
-        // every thread keeps its list entry of the next kJacAhead steps in flight (one L2 round trip per step
-        // would otherwise bound the loop)
-        constexpr int kJacAhead = 4;
-        int32_t pre_row[kJacAhead]; uint16_t pre_val[kJacAhead];
-#pragma unroll
-        for (int u = 0; u < kJacAhead; ++u) {
-          pre_row[u] = 0; pre_val[u] = 0;
-          if (u < nb && tid < st.n[u]) { pre_row[u] = csc_row[st.b[u] + tid]; pre_val[u] = csc_val[st.b[u] + tid]; }
+        if (tid == 0) {
+          int run = 0, fit = 0;
+          st.pre[0] = 0;
+          for (int e = 0; e < nb; ++e) {
+            if (run + st.n[e] > kJacListCap) break;
+            run += st.n[e];
+            st.pre[++fit] = run;
+          }
+          st.fit = fit;
         }
-        for (int e0 = 0; e0 < nb; e0 += kJacAhead) {
+        __syncthreads();
+        const int fit = st.fit;
+        if (fit == 0) {
+          // a single inverted list longer than the staging buffer: walk it straight from global memory
+          const int n = st.n[0];
+          const int64_t b = st.b[0];
+          const __half vik = __ushort_as_half(st.v[0]);
+          for (int u = lane; u < n; u += 32) {
+            const int g = csc_row[b + u];
+            const int c = g - Q - t0;
+            if (c >= 0 && c < tn && (g & (kJacWarps - 1)) == w) jac_apply(acc, c, csc_val[b + u], vik);
+          }
+          e0 += 1;
+          continue;
+        }
+        // Stage the lists of these steps bucketed by OWNER THREAD (g mod 512): every accumulator entry is only
+        // ever touched by its owner, which applies its few entries in step order -> no barrier, no atomics on acc.
+        const int total = st.pre[fit];
+        st.own_cnt[tid] = 0;
+        __syncthreads();
+        constexpr int kPer = kJacListCap / kJacThreads;   // entries per thread per round
+        uint64_t mine[kPer];
+        int owner[kPer];
 #pragma unroll
-          for (int u = 0; u < kJacAhead; ++u) {
-            const int e = e0 + u;
-            if (e < nb) {   // block-uniform
-              const int n = st.n[e];
-              const int64_t b = st.b[e];
-              const __half vik = __ushort_as_half(st.v[e]);
-              const int32_t cur_row = pre_row[u]; const uint16_t cur_val = pre_val[u];
-              if (e + kJacAhead < nb && tid < st.n[e + kJacAhead]) {
-                pre_row[u] = csc_row[st.b[e + kJacAhead] + tid];
-                pre_val[u] = csc_val[st.b[e + kJacAhead] + tid];
-              }
-              if (tid < n) {
-                const int c = cur_row - Q - t0;
-                if (c >= 0 && c < tn) {
-                  const __half vg = __ushort_as_half(cur_val);
-                  const __half mn = __hlt(vg, vik) ? vg : vik;
-                  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
-                }
-              }
-              for (int uu = tid + kJacThreads; uu < n; uu += kJacThreads) {   // lists longer than the CTA (rare)
-                const int c = csc_row[b + uu] - Q - t0;
-                if (c >= 0 && c < tn) {
-                  const __half vg = __ushort_as_half(csc_val[b + uu]);
-                  const __half mn = __hlt(vg, vik) ? vg : vik;
-                  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
-                }
-              }
-              __syncthreads();
+        for (int j = 0; j < kPer; ++j) {
+          const int idx = tid + j * kJacThreads;
+          owner[j] = -1;
+          if (idx < total) {
+            int lo = 0, hi = fit;                       // step s with pre[s] <= idx < pre[s+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.pre[mid] <= idx) lo = mid; else hi = mid; }
+            const int64_t src = st.b[lo] + (idx - st.pre[lo]);
+            const int g = csc_row[src];
+            const int c = g - Q - t0;
+            if (c >= 0 && c < tn) {
+              owner[j] = g & (kJacThreads - 1);
+              mine[j] = ((uint64_t)lo << 48) | ((uint64_t)csc_val[src] << 32) | (uint32_t)c;   // sorts by step first
+              atomicAdd(&st.own_cnt[owner[j]], 1);
             }
           }
         }
+        __syncthreads();
+        {
+          int tot;
+          const int off = block_exclusive_scan(st.own_cnt[tid], st.scan, &tot);
+          st.own_off[tid] = off;
+          if (tid == kJacThreads - 1) st.own_off[kJacThreads] = tot;
+          st.own_cnt[tid] = 0;   // reused as the fill cursor
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+          if (owner[j] >= 0) ent[st.own_off[owner[j]] + atomicAdd(&st.own_cnt[owner[j]], 1)] = mine[j];
+        __syncthreads();
+        {
+          const int a0 = st.own_off[tid], a1 = st.own_off[tid + 1];
+          for (int x = a0 + 1; x < a1; ++x) {          // insertion sort of a handful of entries by step
+            const uint64_t key = ent[x];
+            int y = x - 1;
+            while (y >= a0 && ent[y] > key) { ent[y + 1] = ent[y]; --y; }
+            ent[y + 1] = key;
+          }
+          for (int x = a0; x < a1; ++x) {
+            const uint64_t en = ent[x];
+            jac_apply(acc, (int)(uint32_t)(en & 0xffffffffu), (uint16_t)((en >> 32) & 0xffffu), __ushort_as_half(st.v[(int)(en >> 48)]));
+          }
+        }
+        e0 += fit;
       }
       __syncthreads();
-      // Jaccard + blend, four independent columns per thread per trip (coalesced 128-byte warp accesses)
-      for (int c0 = tid; c0 < tn; c0 += kJacThreads * 4) {
-        float dv[4];
+      // Jaccard + blend, eight independent columns per thread per trip (coalesced 128-byte warp accesses)
+      constexpr int JU = 8;
+      for (int c0 = tid; c0 < tn; c0 += kJacThreads * JU) {
+        float dv[JU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < JU; ++j) {
           const int c = c0 + j * kJacThreads;
           dv[j] = c < tn ? drow[t0 + c] : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < JU; ++j) {
           const int c = c0 + j * kJacThreads;
           if (c < tn) {
             const float a = __half2float(acc[c]);
-            const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
-            const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
-            const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
-            const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
+            __half jl = one_minus_lambda;   // untouched g (the common case): temp_min = 0 -> jaccard = 1 -> fp16(1 * fp16(1-lambda))
+            if (a != 0.f) {                 // (also keeps 0 / 2 off the slow path of the IEEE division)
+              const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
+              const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
+              const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
+              jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
+            }
             const float dn = dv[j] / rmax;                                           // original_dist[i, Q+g]   (:46,72)
             orow[t0 + c] = __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value)); // (:95) two roundings, no FMA contraction
           }
@@ -543,12 +598,8 @@ extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, c
   MPREID_REQUIRE(R > 0 && N > 1 && R <= N && N < INT32_MAX && ld_dist >= N, "rerank_build_v0: bad shape R=%lld N=%lld", (long long)R, (long long)N);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && K >= k1 + 1, "rerank_build_v0: k1 must be in [1, %d] and K >= k1+1", kMaxK1);
   const int sms = sm_count_of_current_device();
-  static bool attr_v0 = false;
   const int v0_smem = (int)sizeof(V0Smem);
-  if (!attr_v0) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
-    attr_v0 = true;
-  }
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
   const int Keff = (int)(K < N ? K : N);
   const int64_t grid = R < (int64_t)sms * 16 ? R : (int64_t)sms * 16;
   k_build_v0<<<(unsigned)grid, kV0Threads, v0_smem, (cudaStream_t)stream>>>(dist_rows, ld_dist, row_ids, (int)R, k1, K, Keff, nbr_all,
@@ -601,14 +652,10 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
   const int64_t n_tiles = ceil_div(G, kJacMaxTile);
   int tile_cols = (int)ceil_div(G, n_tiles);
   tile_cols = (tile_cols + 7) & ~7;
-  const int jac_smem = (int)sizeof(JacStage) + tile_cols * 2;
-  static bool attr_jac = false;
-  if (!attr_jac) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(JacStage) + kJacMaxTile * 2 + 16));
-    attr_jac = true;
-  }
-  const int ctas_per_sm = jac_smem <= 24 * 1024 ? 4 : (jac_smem <= 54 * 1024 ? 3 : 2);
+  const int jac_smem = (int)sizeof(JacStage) + kJacListCap * 8 + 16 + tile_cols * 2;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(JacStage) + kJacListCap * 8 + kJacMaxTile * 2 + 32));
+  const int ctas_per_sm = jac_smem <= 54 * 1024 ? 4 : (jac_smem <= 73 * 1024 ? 3 : 2);
   const int64_t jac_grid = Qs < (int64_t)sms * ctas_per_sm ? Qs : (int64_t)sms * ctas_per_sm;
   k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist_qrows, ld_dist, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
                                                                v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,

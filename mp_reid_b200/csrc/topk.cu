@@ -184,14 +184,15 @@ k_row_topk(const float* __restrict__ dist, int64_t ld, int Q, int G, int k, cons
            int32_t* __restrict__ idx_out, float* __restrict__ val_out, int cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;   // 8 for the usual small k, fewer when the per-warp buffers grow with k
   WarpSel w;
   w.q = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * cap;
-  w.hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTopkWarps * cap * 8) + warp * 256;
+  w.hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)warps * cap * 8) + warp * 256;
   w.lane = lane;
   const int keff = min(k, G);
   const int drain_at = cap - kTopkChunk;   // cut before a full chunk could overflow the buffer
   const bool has_scale = row_scale != nullptr;
-  for (int row_i = blockIdx.x * kTopkWarps + warp; row_i < Q; row_i += gridDim.x * kTopkWarps) {
+  for (int row_i = blockIdx.x * warps + warp; row_i < Q; row_i += gridDim.x * warps) {
     const float* row = dist + (int64_t)row_i * ld;
     const float r = has_scale ? row_scale[row_i] : 1.0f;
     RowState st;
@@ -315,18 +316,18 @@ extern "C" int mpreid_row_topk(const float* dist, int64_t ld_dist, int64_t Q, in
   // per-warp candidate buffer: max(2k, 256) entries between cuts plus one full chunk
   int cap = (2 * k > 256 ? 2 * k : 256) + kTopkChunk;
   cap = (cap + 31) / 32 * 32;
-  const int smem = kTopkWarps * (cap * 8 + 256 * 4);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_row_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  const int per_warp = cap * 8 + 256 * 4;
+  int warps = (220 * 1024) / per_warp;            // as many warps per CTA as shared memory allows, at most 8
+  warps = warps > kTopkWarps ? kTopkWarps : warps;
+  MPREID_REQUIRE(warps >= 1, "row_topk: k=%d needs more shared memory than one SM has", k);
+  const int smem = warps * per_warp;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_row_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int sms = sm_count_of_current_device();
   int ctas_per_sm = (220 * 1024) / (smem + 1024);
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
-  const int64_t want = ceil_div(Q, kTopkWarps);
+  const int64_t want = ceil_div(Q, warps);
   const int64_t grid = want < (int64_t)sms * ctas_per_sm ? want : (int64_t)sms * ctas_per_sm;
-  k_row_topk<<<(unsigned)grid, kTopkThreads, smem, (cudaStream_t)stream>>>(dist, ld_dist, (int)Q, (int)G, k, row_scale, idx, val, cap);
+  k_row_topk<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(dist, ld_dist, (int)Q, (int)G, k, row_scale, idx, val, cap);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

@@ -228,7 +228,6 @@ def rank_eval_async(dist: torch.Tensor, q_pid, g_pid, q_cam=None, g_cam=None, ju
                                      _ptr(q_cam), _ptr(g_cam), junk_mode, res.first_hit.data_ptr(), res.ap.data_ptr(),
                                      res.num_rel.data_ptr(), ws.data_ptr(), nbytes, cap, res.status.data_ptr(), _stream()),
                 "rank_eval")
-    res._retry = (dist, q_pid, g_pid, q_cam, g_cam, junk)
     return res
 
 

@@ -188,7 +188,7 @@ def test_eval_func_error_and_note_conventions(capsys):
 def test_row_topk_equals_stable_argsort_prefix():
     rng = np.random.RandomState(5)
     for (Q, G, k, quant, scaled) in [(50, 5000, 21, None, True), (20, 30000, 100, 128, True), (9, 37, 51, 8, False),
-                                      (3, 100003, 51, None, True), (4, 2500, 1000, 16, True)]:
+                                      (3, 100003, 51, None, True), (4, 2500, 1000, 16, True), (3, 9000, 2048, None, True)]:
         d = (rng.rand(Q, G).astype(np.float32) + 0.25)
         if quant:
             d = np.round(d * quant).astype(np.float32) / quant
