@@ -154,9 +154,19 @@ def run_ours(args, data, workload):
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
-        # keep stdout to the ONE JSON line: NCCL prints its version banner / warnings to stdout unless told otherwise
-        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("MPREID_NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to fd 1 when the communicator is created,
+        # so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     qf, gf, q_pid, g_pid, q_cam, g_cam = data
     Q, G, D = qf.shape[0], gf.shape[0], qf.shape[1]
     prec, junk, metric = args.precision, args.junk, args.metric
