@@ -173,10 +173,16 @@ def dist_matrix_all_pairs(x: Prepared, precision: str | None = None, out: torch.
     return out
 
 
+_RESERVED_LABEL = np.iinfo(np.int64).min   # the empty-slot marker of the label hash table (include/mpreid_b200.h)
+
+
 def _labels(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.int64, non_blocking=True)
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int64)).to(device, non_blocking=True)
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.int64)
+    if a.size and a.min() == _RESERVED_LABEL:
+        raise ValueError("pid / camid value INT64_MIN is reserved")
+    return torch.from_numpy(a).to(device, non_blocking=True)
 
 
 _pos_capacity_hint = {}

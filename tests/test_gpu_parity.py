@@ -501,3 +501,46 @@ def test_triplet_distance_and_hard_mining_forward():
         want_an, want_ni = torch.where(~is_pos, dm, torch.full_like(dm, float("inf"))).min(1)
         assert torch.equal(ap.cpu(), want_ap) and torch.equal(an.cpu(), want_an)
         assert torch.equal(dm[torch.arange(P * K), pi.cpu()], want_ap) and torch.equal(dm[torch.arange(P * K), ni.cpu()], want_an)
+
+
+# ------------------------------------------------------------------------------------ small / degenerate shapes
+def test_rerank_tiny_sets_fewer_samples_than_k1():
+    """N <= k1: the neighbour lists are shorter than k1+1 (utils/reranking.py:53 just slices what exists)."""
+    for (nq, ng, k1, k2) in [(3, 9, 20, 6), (2, 5, 7, 3), (1, 30, 20, 1)]:
+        qf, gf, *_ = synth.make_set(nq, ng, 16, 4, 2, seed=31 + nq, sigma=0.8)
+        f = orc.l2_normalize(torch.cat([qf, gf]).numpy())
+        dall = orc.pairwise_sq_all(f)
+        want = orc.re_ranking_from_dist(dall, nq, k1, k2, 0.3)
+        got = E.rerank_from_dist(dev(dall.T.copy()), nq, k1, k2, 0.3).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-3, (nq, ng, k1, k2, np.abs(got - want).max())
+
+
+def test_rank_eval_many_random_small_cases():
+    """Seeded sweep over small shapes: ties, single-element galleries, all-positive / no-positive rows, odd strides."""
+    rng = np.random.RandomState(77)
+    for case in range(60):
+        Q, G = int(rng.randint(1, 40)), int(rng.randint(1, 700))
+        n_id = int(rng.randint(1, 8))
+        quant = [None, 2, 8, 64][case % 4]
+        d = rng.randn(Q, G).astype(np.float32)
+        if quant:
+            d = np.round(d * quant).astype(np.float32) / quant
+        q_pid, g_pid = rng.randint(0, n_id, Q), rng.randint(0, n_id, G)
+        q_cam, g_cam = rng.randint(0, 2, Q), rng.randint(0, 2, G)
+        for junk in ["none", "pid_cam"]:
+            try:
+                want = orc.rank_eval(d, q_pid, g_pid, q_cam, g_cam, junk=junk)
+            except (AssertionError, ValueError):
+                continue
+            # a padded device buffer exercises leading dimensions != G
+            buf = torch.full((Q, G + 5), float("nan"), device=DEV)
+            buf[:, :G] = dev(d)
+            fh, ap, nr = E.rank_eval(buf[:, :G], q_pid, g_pid, q_cam, g_cam, junk=junk)
+            assert np.array_equal(fh.cpu().numpy(), want["first_hit"]), (case, Q, G, junk)
+            assert np.array_equal(nr.cpu().numpy(), want["num_rel"]) and np.array_equal(ap.cpu().numpy(), want["ap"]), (case, Q, G, junk)
+
+
+def test_reserved_label_is_rejected():
+    d = torch.rand(2, 4, device=DEV)
+    with pytest.raises(ValueError, match="reserved"):
+        E.rank_eval(d, np.array([1, np.iinfo(np.int64).min]), np.array([1, 2, 3, 4]))
