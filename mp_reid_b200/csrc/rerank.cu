@@ -112,35 +112,55 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* sh /*[33]*/, int
 
 // ----------------------------------------------------------------------------------- V0 rows
 static constexpr int kV0Threads = 128;
-static constexpr int kV0MaxK = kMaxK1 + 1;
-static constexpr int kV0MaxHalf = kMaxK1 / 2 + 2;
-static constexpr int kV0ListCap = 8192;  // >= next_pow2((k1+1)(half+1)) for k1 <= 100
 
+// Shared-memory view of one V0 CTA, carved from dynamic shared memory with sizes that follow k1 (252 list
+// entries for k1=20 but 5,353 for k1=100): small k1 -> a few KB per CTA -> many resident CTAs to hide the
+// dependent neighbour-list loads.
 struct V0Smem {
-  int32_t fwd[kV0MaxK];
-  int32_t recip[kV0MaxK];
-  int32_t cand_cnt[kV0MaxK], cand_common[kV0MaxK];
-  uint8_t flag[kV0MaxK * kV0MaxHalf];
-  int32_t list[kV0ListCap];
-  float w[kV0MaxK * (kV0MaxHalf + 1)];
-  int32_t n_recip, n_list, n_out;
-  float wsum;
-  int sh[33];
+  int32_t* fwd; int32_t* recip; int32_t* cand_cnt; int32_t* cand_common;   // [K1]
+  int32_t* list;   // [list_cap] (power of two >= K1 * (half + 1))
+  float* w;        // [K1 * (half + 1)]
+  uint8_t* flag;   // [K1 * half]
+  int32_t* ctrl;   // n_recip, n_list, n_out, wsum bits
+  int* sh;         // [33]
 };
+struct V0Sizes { int K1, half, list_cap, bytes; };
+__host__ __device__ __forceinline__ V0Sizes v0_sizes(int k1) {
+  V0Sizes z;
+  z.K1 = k1 + 1;
+  z.half = round_half_even_div2(k1) + 1;
+  z.list_cap = (int)next_pow2_u32((uint32_t)(z.K1 * (z.half + 1)));
+  const int words = 4 * z.K1 + z.list_cap + z.K1 * (z.half + 1) + 4 + 33;
+  z.bytes = words * 4 + ((z.K1 * z.half + 15) & ~15);
+  return z;
+}
+__device__ __forceinline__ V0Smem v0_carve(unsigned char* base, const V0Sizes& z) {
+  V0Smem s;
+  int32_t* p = reinterpret_cast<int32_t*>(base);
+  s.fwd = p; p += z.K1; s.recip = p; p += z.K1; s.cand_cnt = p; p += z.K1; s.cand_common = p; p += z.K1;
+  s.list = p; p += z.list_cap;
+  s.w = reinterpret_cast<float*>(p); p += z.K1 * (z.half + 1);
+  s.ctrl = p; p += 4;
+  s.sh = reinterpret_cast<int*>(p); p += 33;
+  s.flag = reinterpret_cast<uint8_t*>(p);
+  return s;
+}
 
 __global__ void __launch_bounds__(kV0Threads)
 k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ row_ids, int R, int k1, int K, int Keff_in,
            const int32_t* __restrict__ nbr, const float* __restrict__ rowmax,
            int32_t* __restrict__ v0_col, uint16_t* __restrict__ v0_val, int32_t* __restrict__ v0_len, int C0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  V0Smem& s = *reinterpret_cast<V0Smem*>(smem_raw);
+  const V0Smem s = v0_carve(smem_raw, v0_sizes(k1));
+  int32_t& n_recip = s.ctrl[0]; int32_t& n_list = s.ctrl[1]; int32_t& n_out = s.ctrl[2];
+  float& wsum_s = *reinterpret_cast<float*>(&s.ctrl[3]);
   const int tid = threadIdx.x;
   const int K1 = min(k1 + 1, Keff_in);                       // forward list length (:53)
   const int half = min(round_half_even_div2(k1) + 1, Keff_in);  // candidate list length (:60)
   // il = row of this block of the all-pairs matrix, i = the sample it belongs to (global index)
   for (int il = blockIdx.x; il < R; il += gridDim.x) {
     const int i = row_ids ? row_ids[il] : il;
-    if (tid == 0) { s.n_recip = 0; s.n_list = 0; }
+    if (tid == 0) { n_recip = 0; n_list = 0; }
     for (int m = tid; m < K1; m += kV0Threads) s.fwd[m] = nbr[(int64_t)i * K + m];
     __syncthreads();
     // reciprocity: i in the first K1 neighbours of fwd[m]   (:54-56)
@@ -148,10 +168,10 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict
       const int32_t* row = nbr + (int64_t)s.fwd[m] * K;
       bool hit = false;
       for (int t = 0; t < K1; ++t) hit |= (row[t] == i);
-      if (hit) { const int p = atomicAdd(&s.n_recip, 1); s.recip[p] = s.fwd[m]; }
+      if (hit) { const int p = atomicAdd(&n_recip, 1); s.recip[p] = s.fwd[m]; }
     }
     __syncthreads();
-    const int nR = s.n_recip;
+    const int nR = n_recip;
     // candidate k-reciprocal sets with the half-size lists  (:58-64)
     for (int p = tid; p < nR * half; p += kV0Threads) {
       const int j = p / half, m = p - j * half;
@@ -175,17 +195,17 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict
     }
     __syncthreads();
     // expansion list = R(i) plus every accepted candidate set  (:65-67), then np.unique (:69)
-    for (int t = tid; t < nR; t += kV0Threads) { const int p = atomicAdd(&s.n_list, 1); s.list[p] = s.recip[t]; }
+    for (int t = tid; t < nR; t += kV0Threads) { const int p = atomicAdd(&n_list, 1); s.list[p] = s.recip[t]; }
     for (int p = tid; p < nR * half; p += kV0Threads) {
       if (!s.flag[p]) continue;
       const int j = p / half, m = p - j * half;
       if ((double)s.cand_common[j] > (2.0 / 3.0) * (double)s.cand_cnt[j]) {
-        const int q = atomicAdd(&s.n_list, 1);
+        const int q = atomicAdd(&n_list, 1);
         s.list[q] = nbr[(int64_t)s.recip[j] * K + m];
       }
     }
     __syncthreads();
-    const int nL = s.n_list;
+    const int nL = n_list;
     const int P = (int)next_pow2_u32((uint32_t)max(nL, 1));
     for (int t = nL + tid; t < P; t += kV0Threads) s.list[t] = INT32_MAX;
     __syncthreads();
@@ -195,10 +215,10 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict
       int n = 0;
       for (int t = 0; t < nL; ++t)
         if (t == 0 || s.list[t] != s.list[t - 1]) s.list[n++] = s.list[t];
-      s.n_out = n;
+      n_out = n;
     }
     __syncthreads();
-    const int nU = s.n_out;
+    const int nU = n_out;
     const float rmax = rowmax[il];
     const float* drow = dist + (int64_t)il * ld;
     for (int t = tid; t < nU; t += kV0Threads) {
@@ -206,9 +226,9 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict
       s.w[t] = (float)exp((double)(-dn));               // np.exp on float32      (:70)
     }
     __syncthreads();
-    if (tid == 0) s.wsum = pairwise_sum_f32(s.w, nU);   // np.sum(weight)         (:71)
+    if (tid == 0) wsum_s = pairwise_sum_f32(s.w, nU);   // np.sum(weight)         (:71)
     __syncthreads();
-    const float wsum = s.wsum;
+    const float wsum = wsum_s;
     // V[i, idx] = fp16(weight / sum); entries that underflow to 0 are not stored (V != 0 tests, :82,88)
     int keep = 0;
     uint16_t hv = 0;
@@ -564,7 +584,7 @@ static size_t carve_finish(FinishWs* w, char* base, int64_t N, int64_t Q, int k1
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return base ? base + o : nullptr; };
   const int C0 = v0_capacity(k1, N);
   const int64_t C1 = v_capacity(k1, k2, N);
-  const int qe_grid = sms * 4;
+  const int qe_grid = sms * 6;   // 6 x 256 threads x 32 KB static smem per SM
   int64_t qe_P = 1;
   while (qe_P < (int64_t)k2 * C0) qe_P <<= 1;
   if (qe_P <= kQeSmemEntries || k2 == 1) qe_P = 0;  // fits shared memory: no global scratch
@@ -598,10 +618,12 @@ extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, c
   MPREID_REQUIRE(R > 0 && N > 1 && R <= N && N < INT32_MAX && ld_dist >= N, "rerank_build_v0: bad shape R=%lld N=%lld", (long long)R, (long long)N);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && K >= k1 + 1, "rerank_build_v0: k1 must be in [1, %d] and K >= k1+1", kMaxK1);
   const int sms = sm_count_of_current_device();
-  const int v0_smem = (int)sizeof(V0Smem);
+  const int v0_smem = v0_sizes(k1).bytes;
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_build_v0, cudaFuncAttributeMaxDynamicSharedMemorySize, v0_smem));
   const int Keff = (int)(K < N ? K : N);
-  const int64_t grid = R < (int64_t)sms * 16 ? R : (int64_t)sms * 16;
+  int v0_ctas = (200 * 1024) / (v0_smem + 1024);
+  v0_ctas = v0_ctas > 16 ? 16 : (v0_ctas < 1 ? 1 : v0_ctas);   // 16 x 128 threads fill an SM
+  const int64_t grid = R < (int64_t)sms * v0_ctas ? R : (int64_t)sms * v0_ctas;
   k_build_v0<<<(unsigned)grid, kV0Threads, v0_smem, (cudaStream_t)stream>>>(dist_rows, ld_dist, row_ids, (int)R, k1, K, Keff, nbr_all,
                                                                             row_max_rows, v0_col, v0_val, v0_len, v0_capacity(k1, N));
   MPREID_CUDA_CHECK(cudaGetLastError());
