@@ -108,35 +108,38 @@ HD double pairwise_leaf(const int32_t* rank, int64_t lo, int64_t n, int a, int b
   return res;
 }
 
-// sum of the length-n vector whose non-zeros sit at positions rank[0..m)-1 (ascending), numpy pairwise order
+// sum of the length-n vector whose non-zeros sit at positions rank[0..m)-1 (ascending), numpy pairwise order.
+// Empty subtrees contribute +0.0 and x + 0.0 == x, so the value is the non-empty leaves (blocks <= 128)
+// combined in the bracketing the halving tree induces: two neighbouring leaves join at their lowest common
+// tree node, deeper joins first.  One descent per non-empty leaf finds both the leaf and the depth at
+// which it parts from its predecessor; a small stack holds the partial sums still waiting for their sibling.
 HD double pairwise_sparse_sum(const int32_t* rank, int m, int64_t n) {
-  struct Frame { int64_t lo, n; int a, b, mid, stage; double left; };
-  Frame st[48];
-  int sp = 1;
-  st[0].lo = 0; st[0].n = n; st[0].a = 0; st[0].b = m; st[0].stage = 0; st[0].mid = 0; st[0].left = 0.0;
-  double ret = 0.0;
-  while (sp > 0) {
-    Frame& f = st[sp - 1];
-    if (f.stage == 0) {
-      if (f.a == f.b) { ret = 0.0; --sp; continue; }
-      if (f.n <= 128) { ret = pairwise_leaf(rank, f.lo, f.n, f.a, f.b); --sp; continue; }
-      int64_t n2 = f.n / 2; n2 -= n2 % 8;
-      f.mid = lower_bound_pos(rank, f.a, f.b, f.lo + n2);
-      f.stage = 1;
-      Frame& c = st[sp++];
-      c.lo = f.lo; c.n = n2; c.a = f.a; c.b = f.mid; c.stage = 0;
-    } else if (f.stage == 1) {
-      f.left = ret;
-      f.stage = 2;
-      int64_t n2 = f.n / 2; n2 -= n2 % 8;
-      Frame& c = st[sp++];
-      c.lo = f.lo + n2; c.n = f.n - n2; c.a = f.mid; c.b = f.b; c.stage = 0;
-    } else {
-      ret = f.left + ret;
-      --sp;
+  if (m <= 0) return 0.0;
+  double val[64];
+  int junc[64];          // junc[j] = depth of the tree node that joins stack entries j-1 and j
+  int sp = 0, a = 0;
+  int64_t prev = -1;     // a position inside the previous non-empty leaf
+  while (a < m) {
+    const int64_t p = (int64_t)rank[a] - 1;
+    int64_t lo = 0, len = n;
+    int depth = 0, d = -1;
+    bool together = prev >= 0;
+    while (len > 128) {
+      int64_t n2 = len / 2; n2 -= n2 % 8;
+      const bool right = p >= lo + n2;
+      if (together && (prev >= lo + n2) != right) { d = depth; together = false; }
+      if (right) { lo += n2; len -= n2; } else { len = n2; }
+      ++depth;
     }
+    int b = a + 1;
+    while (b < m && (int64_t)rank[b] - 1 < lo + len) ++b;
+    const double v = pairwise_leaf(rank, lo, len, a, b);
+    while (sp >= 2 && junc[sp - 1] > d) { val[sp - 2] = val[sp - 2] + val[sp - 1]; --sp; }
+    val[sp] = v; junc[sp] = d; ++sp;
+    prev = p; a = b;
   }
-  return ret;
+  while (sp >= 2) { val[sp - 2] = val[sp - 2] + val[sp - 1]; --sp; }
+  return val[0];
 }
 
 // np.around(k1 / 2) -- round half to even (utils/reranking.py:60)

@@ -10,6 +10,7 @@
 //   label_*        group gallery indices by pid with an open-addressing hash table (arbitrary int64)
 //   rank_count     per query: keys -> sort -> stream row -> ranks of the same-pid entries, junk fix-up
 //   ap_finalize    per query: float64 AP in numpy's pairwise summation order (common.cuh)
+#include <cstddef>
 #include "common.cuh"
 
 namespace mpreid {
@@ -227,7 +228,8 @@ struct RankSmem {
   uint32_t hist[kRankCap + 1];
   uint32_t scratch[kRankThreads];
   uint16_t lut[257];
-  uint2 queue[kWarps][kQueueCap];   // (float bits, gallery index)
+  float qval[kWarps][kQueueCap];      // per-warp candidate queue: row values ...
+  uint32_t qidx[kWarps][kQueueCap];   // ... and their gallery indices
   int32_t misc[4];
 };
 
@@ -236,15 +238,17 @@ struct RowCtx {
   int m; uint32_t omin, tmax; int shift; float tmax_f;
 };
 
-__device__ __forceinline__ void drain_queue(const RowCtx& c, uint2* q, int count, int lane) {
+// One warp's candidate queue, structure-of-arrays so that an insertion is two plain 32-bit stores
+struct WarpQueue { float* val; uint32_t* idx; };
+
+__device__ __forceinline__ void drain_queue(const RowCtx& c, const WarpQueue& q, int count, int lane) {
   for (int e0 = 0; e0 < count; e0 += 32) {   // warp-uniform trip count: every lane reaches match.any
     const int e = e0 + lane;
     int b = -1;
     if (e < count) {
-      const uint2 it = q[e];
-      const uint32_t o = order_key(__uint_as_float(it.x));
+      const uint32_t o = order_key(q.val[e]);
       if (o <= c.tmax) {   // re-check in key space (the float pre-test lets -0.0 / NaN through)
-        const uint64_t key = ((uint64_t)o << 32) | it.y;
+        const uint64_t key = ((uint64_t)o << 32) | q.idx[e];
         int lo = 0, hi = 0;
         if (o >= c.omin) { const uint32_t bin = (o - c.omin) >> c.shift; lo = c.lut[bin]; hi = c.lut[bin + 1]; }
         // keys before lo sit in earlier bins (< key), keys from hi on in later bins (> key): #keys < key is in [lo, hi]
@@ -260,7 +264,62 @@ __device__ __forceinline__ void drain_queue(const RowCtx& c, uint2* q, int count
   }
 }
 
-__device__ __forceinline__ void stream_row(const float* __restrict__ row, int G, const RowCtx& c, uint2* q) {
+// queue append of one row value, hand-scheduled: 5 instructions per element (setp, index add, two stores,
+// cursor add), stores and cursor predicated on "value not above tmax" (unordered passes: NaN is sorted out by the drain)
+static constexpr int kQueueIdxOffset = kWarps * kQueueCap * 4;   // byte distance qval[w][e] -> qidx[w][e]
+static_assert(offsetof(RankSmem, qidx) - offsetof(RankSmem, qval) == kQueueIdxOffset, "queue planes must be adjacent");
+__device__ __forceinline__ void queue_push(uint32_t& cursor, float v, float tmax_f, uint32_t idx) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.leu.f32 p, %1, %2;\n\t"
+      "@p st.shared.f32 [%0], %1;\n\t"
+      "@p st.shared.u32 [%0+%4], %3;\n\t"
+      "@p add.u32 %0, %0, 4;\n\t}"
+      : "+r"(cursor) : "f"(v), "f"(tmax_f), "r"(idx), "n"(kQueueIdxOffset) : "memory");
+}
+// -1 if v is a candidate (not above tmax), else 0
+__device__ __forceinline__ int cand_mask(float v, float tmax_f) {
+  int r;
+  asm("set.leu.s32.f32 %0, %1, %2;" : "=r"(r) : "f"(v), "f"(tmax_f));
+  return r;
+}
+
+// One pass of kRankThreads * U float4 of the row (already in registers): count the candidates (row value
+// not above the largest same-pid value), one warp scan for the queue positions, then predicated (value,
+// index) stores.  FULL = every thread has all U vectors in range (no bounds tests in the steady state).
+template <bool FULL, int U>
+__device__ __forceinline__ void stream_block(const float4 (&x)[U], int v0, int nvec, int head, float tmax_f,
+                                             const RowCtx& c, const WarpQueue& q, int& qcount) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  int n = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (FULL || v0 + u * kRankThreads + tid < nvec)
+      n -= cand_mask(x[u].x, tmax_f) + cand_mask(x[u].y, tmax_f) + cand_mask(x[u].z, tmax_f) + cand_mask(x[u].w, tmax_f);
+  }
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total) {
+    uint32_t cursor = (uint32_t)__cvta_generic_to_shared(q.val + qcount + incl - n);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (FULL || v0 + u * kRankThreads + tid < nvec) {
+        const uint32_t j = (uint32_t)(head + 4 * (v0 + u * kRankThreads + tid));
+        queue_push(cursor, x[u].x, tmax_f, j);
+        queue_push(cursor, x[u].y, tmax_f, j + 1);
+        queue_push(cursor, x[u].z, tmax_f, j + 2);
+        queue_push(cursor, x[u].w, tmax_f, j + 3);
+      }
+    }
+    qcount += total;
+    __syncwarp();
+    if (qcount >= kQueueDrain) { drain_queue(c, q, qcount, lane); qcount = 0; __syncwarp(); }
+  }
+}
+
+__device__ __forceinline__ void stream_row(const float* __restrict__ row, int G, const RowCtx& c, const WarpQueue& q) {
   const int tid = threadIdx.x, lane = tid & 31;
   int qcount = 0;  // warp-uniform
   int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
@@ -279,64 +338,82 @@ __device__ __forceinline__ void stream_row(const float* __restrict__ row, int G,
     int incl = n;
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
     int pos = qcount + incl - n;
-    if (mask & 1u) q[pos++] = make_uint2(__float_as_uint(v[0]), jj[0]);
-    if (mask & 2u) q[pos++] = make_uint2(__float_as_uint(v[1]), jj[1]);
+    if (mask & 1u) { q.val[pos] = v[0]; q.idx[pos] = jj[0]; ++pos; }
+    if (mask & 2u) { q.val[pos] = v[1]; q.idx[pos] = jj[1]; ++pos; }
     qcount += __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
   }
-  for (int v0 = 0; v0 < nvec; v0 += kRankThreads * U) {
-    float4 x[U];
+  constexpr int kStep = kRankThreads * U;
+  // software pipeline: the next block's 64 bytes per thread are in flight while this block is classified
+  float4 cur[U], nxt[U];
+  int v0 = 0;
+  if (kStep <= nvec) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int v = v0 + u * kRankThreads + tid;
-      x[u] = v < nvec ? ldg_stream4(rv + v) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-    }
-    uint32_t mask = 0;
+    for (int u = 0; u < U; ++u) cur[u] = ldg_stream4(rv + u * kRankThreads + tid);
+  }
+  for (; v0 + kStep <= nvec; v0 += kStep) {
+    const int v1 = v0 + kStep;
+    if (v1 + kStep <= nvec) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      mask |= (!(x[u].x > tmax_f) ? 1u : 0u) << (4 * u);
-      mask |= (!(x[u].y > tmax_f) ? 2u : 0u) << (4 * u);
-      mask |= (!(x[u].z > tmax_f) ? 4u : 0u) << (4 * u);
-      mask |= (!(x[u].w > tmax_f) ? 8u : 0u) << (4 * u);
-    }
+      for (int u = 0; u < U; ++u) nxt[u] = ldg_stream4(rv + v1 + u * kRankThreads + tid);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u)   // padding lanes loaded +inf; +inf <= +inf only if tmax_f is +inf: mask them out
-      if (v0 + u * kRankThreads + tid >= nvec) mask &= ~(0xfu << (4 * u));
-    const int n = __popc(mask);
-    int incl = n;
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {
-      int pos = qcount + incl - n;
-      if (mask) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const uint32_t j = head + 4 * (v0 + u * kRankThreads + tid);
-          if (mask & (1u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].x), j);
-          if (mask & (2u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].y), j + 1);
-          if (mask & (4u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].z), j + 2);
-          if (mask & (8u << (4 * u))) q[pos++] = make_uint2(__float_as_uint(x[u].w), j + 3);
-        }
+      for (int u = 0; u < U; ++u) {
+        const int v = v1 + u * kRankThreads + tid;
+        nxt[u] = v < nvec ? ldg_stream4(rv + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      qcount += total;
-      __syncwarp();
-      if (qcount >= kQueueDrain) { drain_queue(c, q, qcount, lane); qcount = 0; __syncwarp(); }
     }
+    stream_block<true, U>(cur, v0, nvec, head, tmax_f, c, q, qcount);
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+  }
+  if (v0 < nvec) {
+    if (v0 == 0) {   // row shorter than one full block: nothing was prefetched
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int v = u * kRankThreads + tid;
+        cur[u] = v < nvec ? ldg_stream4(rv + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    stream_block<false, U>(cur, v0, nvec, head, tmax_f, c, q, qcount);
   }
   if (qcount) drain_queue(c, q, qcount, lane);
+}
+
+// ---- rows with at most 32 same-pid entries (the common case): warp 0 sorts the keys and finishes the row
+//      with shuffles / ballots, so the CTA pays 4 barriers per row instead of ~65
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      const bool take_min = lower == up;
+      key = (take_min == (other < key)) ? other : key;
+    }
+  }
+  return key;
 }
 
 __global__ void __launch_bounds__(kRankThreads)
 k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
              const int64_t* __restrict__ q_cam, const int64_t* __restrict__ g_cam, int junk_mode,
              const int32_t* __restrict__ list, const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_cnt,
-             const int32_t* __restrict__ q_off, const int32_t* __restrict__ status,
+             const int32_t* __restrict__ q_off, int32_t* status,
              int32_t* pos_tmp, int32_t* pos_rank, int32_t* first_hit, int32_t* num_rel, int32_t* row_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RankSmem& s = *reinterpret_cast<RankSmem*>(smem_raw);
   if (status[0] != 0) return;  // workspace overflow: the host re-runs with a larger capacity
   const int tid = threadIdx.x;
-  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+  // rows cost anything between "no candidates" and "every element is one": CTAs take rows from a ticket
+  // counter (status[3], zeroed by k_scan_counts) instead of a fixed stride
+  for (;;) {
+    if (tid == 0) s.misc[1] = atomicAdd(&status[3], 1);
+    __syncthreads();
+    const int q = s.misc[1];
+    __syncthreads();
+    if (q >= Q) break;
     const int cnt = q_cnt[q];
     if (cnt == 0) {
       if (tid == 0) { first_hit[q] = 0; num_rel[q] = 0; row_len[q] = G; }
@@ -346,17 +423,28 @@ k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
     const float* row = dist + (int64_t)q * ld;
     const int64_t qc = junk_mode ? q_cam[q] : 0;
 
+    const bool small = cnt <= 32;   // block-uniform
     for (int c0 = 0; c0 < cnt; c0 += kRankCap) {
       const int m = min(kRankCap, cnt - c0);
       const int P = (int)next_pow2_u32((uint32_t)m);
-      for (int i = tid; i < P; i += kRankThreads) {
-        uint64_t key = ~0ull;
-        if (i < m) { const int32_t j = list[start + c0 + i]; key = make_key(row[j], (uint32_t)j); }
-        s.keys[i] = key;
+      if (small) {
+        if (tid < 32) {
+          uint64_t key = ~0ull;
+          if (tid < m) { const int32_t j = list[start + tid]; key = make_key(row[j], (uint32_t)j); }
+          s.keys[tid] = warp_sort_u64(key, tid);
+        }
+        for (int i = tid; i <= m; i += kRankThreads) s.hist[i] = 0;
+        __syncthreads();
+      } else {
+        for (int i = tid; i < P; i += kRankThreads) {
+          uint64_t key = ~0ull;
+          if (i < m) { const int32_t j = list[start + c0 + i]; key = make_key(row[j], (uint32_t)j); }
+          s.keys[i] = key;
+        }
+        for (int i = tid; i <= m; i += kRankThreads) s.hist[i] = 0;
+        __syncthreads();
+        bitonic_sort_u64<kRankThreads>(s.keys, P);
       }
-      for (int i = tid; i <= m; i += kRankThreads) s.hist[i] = 0;
-      __syncthreads();
-      bitonic_sort_u64<kRankThreads>(s.keys, P);
       RowCtx c;
       c.keys = s.keys; c.lut = s.lut; c.hist = s.hist; c.m = m;
       c.tmax = (uint32_t)(s.keys[m - 1] >> 32);
@@ -367,19 +455,45 @@ k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
       c.tmax_f = c.tmax == 0xffffffffu ? INFINITY : order_key_inv(c.tmax);
       {
         // lut[b] = #keys whose 32-bit order key is below the first value of bin b; lut[256] = m
-        const uint64_t lower = (uint64_t)c.omin + ((uint64_t)tid << c.shift);
-        int lo = 0, hi = m;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if ((uint64_t)(s.keys[mid] >> 32) < lower) lo = mid + 1; else hi = mid;
+        for (int b = tid; b < 256; b += kRankThreads) {
+          const uint64_t lower = (uint64_t)c.omin + ((uint64_t)b << c.shift);
+          int lo = 0, hi = m;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint64_t)(s.keys[mid] >> 32) < lower) lo = mid + 1; else hi = mid;
+          }
+          s.lut[b] = (uint16_t)lo;
         }
-        s.lut[tid] = (uint16_t)lo;
         if (tid == 0) s.lut[256] = (uint16_t)m;
       }
       __syncthreads();
-      stream_row(row, G, c, s.queue[tid >> 5]);
+      stream_row(row, G, c, WarpQueue{s.qval[tid >> 5], s.qidx[tid >> 5]});
       __syncthreads();
 
+      if (small) {
+        // warp 0: ranks = inclusive scan of the interval counts; junk entries drop out and shift the kept ranks
+        if (tid < 32) {
+          uint32_t r = tid < m ? s.hist[tid] : 0u;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, r, o); if (tid >= o) r += y; }
+          bool junk = false;
+          if (tid < m && junk_mode) junk = g_cam[(int32_t)(s.keys[tid] & 0xffffffffu)] == qc;
+          const unsigned jm = __ballot_sync(0xffffffffu, junk);
+          const int jb = __popc(jm & (0xffffffffu >> (31 - tid)));   // junk among sorted positions <= tid
+          if (tid < m && !junk) pos_rank[off + tid - jb] = (int32_t)r - jb;
+          const unsigned kept = __ballot_sync(0xffffffffu, tid < m && !junk);
+          const int first = kept ? __ffs(kept) - 1 : 0;
+          const int32_t r_first = (int32_t)__shfl_sync(0xffffffffu, r, first) - __popc(jm & (0xffffffffu >> (31 - first)));
+          if (tid == 0) {
+            const int nj = __popc(jm);
+            num_rel[q] = cnt - nj;
+            row_len[q] = G - nj;
+            first_hit[q] = kept ? r_first : 0;
+          }
+        }
+        __syncthreads();
+        continue;
+      }
       // ---- rank of sorted key i = #row entries <= key i
       block_inclusive_scan<kRankThreads>(s.hist, m, s.scratch);
       for (int i = tid; i < m; i += kRankThreads) {
@@ -390,6 +504,7 @@ k_rank_count(const float* __restrict__ dist, int64_t ld, int Q, int G,
       }
       __syncthreads();
     }
+    if (small) continue;
 
     // ---- junk fix-up: kept rank = rank - #junk ranked before; compact the kept ranks (ascending)
     if (cnt <= kRankCap) {

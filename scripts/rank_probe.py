@@ -18,3 +18,9 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(50): r = E.rank_eval_async(d, *lab, "none")
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(8)
+# per-kernel device time inside the live (back-to-back) sequence
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(10): r = E.rank_eval_async(d, *lab, "none")
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))

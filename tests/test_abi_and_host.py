@@ -53,6 +53,29 @@ def test_host_average_precision_bit_exact_vs_numpy():
         assert got == ref, (n, m)
 
 
+def test_host_average_precision_dense_runs_and_block_edges():
+    """Runs of consecutive hits, hits on both sides of the 8/128-element block edges, every element a hit."""
+    lib = L.load()
+    rng = np.random.RandomState(5)
+    for t in range(160):
+        n = int(rng.randint(1, 1500000)) if t % 2 else int(rng.randint(1, 5000))
+        mode = t % 4
+        if mode == 0:
+            pos = np.sort(rng.choice(n, int(rng.randint(1, min(n, 3000) + 1)), replace=False))
+        elif mode == 1:
+            m = int(rng.randint(1, min(n, 500) + 1)); st = int(rng.randint(0, n - m + 1)); pos = np.arange(st, st + m)
+        elif mode == 2:
+            c = rng.choice(n, min(n, int(rng.randint(1, 200))), replace=False)
+            pos = np.unique(np.clip(np.concatenate([c, c + 1, c + 7, c + 8, c + 127, c + 128]), 0, n - 1))
+        else:
+            pos = np.arange(n) if n < 20000 else np.sort(rng.choice(n, 20000, replace=False))
+        row = np.zeros(n, np.int32); row[pos] = 1
+        tmp = row.cumsum() / (np.arange(1, n + 1) * 1.0)
+        ref = (tmp * row).sum() / row.sum()
+        ranks = (pos + 1).astype(np.int32)
+        assert lib.mpreid_host_average_precision(ranks.ctypes.data, len(pos), n) == ref, (n, mode)
+
+
 def test_host_order_keys_sort_like_numpy_stable():
     lib = L.load()
     rng = np.random.RandomState(1)
