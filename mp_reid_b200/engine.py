@@ -63,8 +63,10 @@ class Prepared:
                         s(self.hh), s(self.hl), s(self.hscale))
 
 
-def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, keep_xn: bool = True) -> Prepared:
-    """F.normalize + squared norms + operand planes in one pass (utils/metrics.py:10-11,114)."""
+def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, keep_xn: bool = True,
+              xn_out: torch.Tensor | None = None) -> Prepared:
+    """F.normalize + squared norms + operand planes in one pass (utils/metrics.py:10-11,114).
+    `xn_out` ([n, D] fp32 rows, unit column stride) receives the (normalised) rows instead of a new tensor."""
     require_cuda()
     lib = L.load()
     precision = (precision or default_precision()).lower()
@@ -79,7 +81,11 @@ def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, ke
     pad = 64 if prec in (L.BF16, L.X3FP16, L.X2FP16) else 32
     Dp = (D + pad - 1) // pad * pad
     need_xn = keep_xn or prec == L.FP32_SIMT
-    xn = torch.empty((n, D), dtype=torch.float32, device=dev) if need_xn else None
+    if xn_out is not None:
+        assert xn_out.is_cuda and xn_out.dtype == torch.float32 and xn_out.shape == (n, D) and xn_out.stride(1) == 1
+        xn = xn_out
+    else:
+        xn = torch.empty((n, D), dtype=torch.float32, device=dev) if need_xn else None
     sqnorm = torch.empty((n,), dtype=torch.float32, device=dev)
     norm = torch.empty((n,), dtype=torch.float32, device=dev)
     hi = lo = bf = hh = hl = hscale = None
@@ -93,7 +99,7 @@ def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, ke
     elif prec == L.BF16:
         bf = torch.empty((n, Dp), dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.mpreid_prep_rows(x.data_ptr(), n, D, x.stride(0), int(bool(normalize)), _ptr(xn), D, sqnorm.data_ptr(),
+        L.check(lib.mpreid_prep_rows(x.data_ptr(), n, D, x.stride(0), int(bool(normalize)), _ptr(xn), xn.stride(0) if xn is not None else D, sqnorm.data_ptr(),
                                      norm.data_ptr(), _ptr(hi), _ptr(lo), _ptr(bf), _ptr(hh), _ptr(hl), _ptr(hscale), Dp,
                                      _stream()), "prep_rows")
     return Prepared(n, D, Dp, xn, sqnorm, norm, hi, lo, bf, hh, hl, hscale)

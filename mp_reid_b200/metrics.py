@@ -278,11 +278,21 @@ class R1_mAP_eval():
             q = E.prep_rows(torch.cat([t for _, t in q_parts], dim=0) if len(q_parts) != 1 else q_parts[0][1],
                             normalize=norm, precision=self._precision, keep_xn=True)
             dist = E.alloc_dist(nq, num_g, q.sqnorm.device)
-            chunk_rows = int(os.environ.get("MPREID_CHUNK_ROWS", "8192"))
-            # gallery chunks: >= chunk_rows rows each, cut at multiples of 32 rows so that every column
-            # block of the distance matrix starts 128-byte aligned (vector stores); batches are split by view
-            gf_parts, off = [], 0
-            pend, pend_rows, last_bi = [], 0, -1
+            chunk_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32)
+            # gallery chunks of chunk_rows rows, cut at multiples of 32 rows so that every column block of
+            # the distance matrix starts 128-byte aligned (vector stores); batches are split by view.  The
+            # last chunks halve down to ~1k rows: the GEMM of a chunk can only start when its last row has
+            # arrived, so the size of the final chunk is what is left to do after the last host->device copy.
+            sizes, rem = [], num_g
+            while rem > 0:
+                sz = chunk_rows if rem > 2 * chunk_rows else max(min(1024, chunk_rows), (rem // 2) // 32 * 32)
+                if rem - sz < 512:
+                    sz = rem
+                sizes.append(sz)
+                rem -= sz
+            gf = torch.empty((num_g, q.D), dtype=torch.float32, device=q.sqnorm.device)   # normalised gallery rows (returned)
+            off = 0
+            pend, pend_rows, last_bi, si = [], 0, -1, 0
 
             def flush(rows_out):
                 nonlocal pend, pend_rows, off
@@ -295,9 +305,8 @@ class R1_mAP_eval():
                     else:
                         rest.append(t)
                 blk = take[0] if len(take) == 1 else torch.cat(take, dim=0)
-                g = E.prep_rows(blk, normalize=norm, precision=self._precision, keep_xn=True)
+                g = E.prep_rows(blk, normalize=norm, precision=self._precision, xn_out=gf[off:off + rows_out])
                 E.dist_matrix(q, g, self._metric, self._precision, out=dist[:, off:off + rows_out])
-                gf_parts.append(g.xn)
                 off += rows_out
                 pend, pend_rows = rest, pend_rows - rows_out
 
@@ -305,11 +314,9 @@ class R1_mAP_eval():
                 self._wait(last_bi + 1, bi + 1)
                 last_bi = bi
                 pend.append(t); pend_rows += t.shape[0]
-                while pend_rows >= chunk_rows:
-                    flush(pend_rows // 32 * 32 if pend_rows // 32 * 32 >= chunk_rows else pend_rows)
-            if pend_rows:
-                flush(pend_rows)
+                while si < len(sizes) and pend_rows >= sizes[si]:
+                    flush(sizes[si])
+                    si += 1
             qf = q.xn
-            gf = gf_parts[0] if len(gf_parts) == 1 else torch.cat(gf_parts, dim=0)
         cmc, mAP = _eval_device(dist, q_pids, g_pids, q_camids, g_camids, 50, self._junk)  # :132 (max_rank is not forwarded)
         return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, qf, gf
