@@ -21,6 +21,7 @@
 // Tiles are visited band-major (16 m-blocks per band, m fastest) so the query band stays in L2 and
 // every gallery tile is fetched from HBM once per band.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "epilogue.cuh"
 
@@ -103,6 +104,54 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) flavours: two CTAs of a cluster on one TPC share one 256x256 tile; each loads
+//      its own 128 query rows and HALF of the gallery rows, the leader (cluster rank 0) issues the MMAs
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address) in the CTA with cluster rank `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// data lands in this CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int PREC>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (PREC == MPREID_3XTF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 
 template <int PREC>
@@ -217,38 +266,96 @@ __device__ __forceinline__ TileCoord sym_decode_tile(int tile, int m_blocks, int
   return t;
 }
 
+// CTA-pair symmetric mode: square 256 x 256 pair tiles (mp, n) with n >= mp, bands of BAND/2 pair rows;
+// inside a band the first h columns form a triangle (column j holds rows 0..j), the rest are full.
+__host__ __device__ __forceinline__ int sym_pair_band_tiles(int b, int Mp, int* h_out) {
+  constexpr int PB = BAND / 2;
+  const int p0 = b * PB;
+  const int h = (PB < Mp - p0) ? PB : (Mp - p0);
+  if (h_out) *h_out = h;
+  return h * (h + 1) / 2 + (Mp - p0 - h) * h;
+}
+__host__ __device__ __forceinline__ int sym_pair_total(int Mp) {
+  int t = 0;
+  for (int b = 0; b * (BAND / 2) < Mp; ++b) t += sym_pair_band_tiles(b, Mp, nullptr);
+  return t;
+}
+// -> m_blk = pair row (units of 256 rows), n_blk = column block
+__device__ __forceinline__ TileCoord sym_pair_decode(int pt, int Mp) {
+  int b = 0, h = 0;
+  for (;; ++b) {
+    const int tb = sym_pair_band_tiles(b, Mp, &h);
+    if (pt < tb) break;
+    pt -= tb;
+  }
+  const int p0 = b * (BAND / 2);
+  TileCoord t;
+  const int tri = h * (h + 1) / 2;
+  if (pt < tri) {
+    int j = 0;
+    while (pt >= j + 1) { pt -= j + 1; ++j; }
+    t.n_blk = p0 + j; t.m_blk = p0 + pt;
+  } else {
+    pt -= tri;
+    t.n_blk = p0 + h + pt / h; t.m_blk = p0 + pt % h;
+  }
+  return t;
+}
+
+// tile -> (128-row query block, 256-column gallery block) of THIS CTA
+template <bool CTA2>
+__device__ __forceinline__ TileCoord tile_coord(int tile, int cta_rank, int m_blocks, int n_blocks, int symmetric) {
+  if (!CTA2) return symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
+  if (!symmetric) return decode_tile(tile + cta_rank, m_blocks, n_blocks);
+  TileCoord t = sym_pair_decode(tile >> 1, m_blocks >> 1);
+  t.m_blk = 2 * t.m_blk + cta_rank;
+  return t;
+}
+
 struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int PREC, int ROW_BYTES, int METRIC, bool VEC>
+// CTA-pair pipeline depth: as many stages as fit 192 KB (3 x 64 KB for the split-fp16 / TF32 modes)
+__host__ __device__ constexpr int pair_stages(int stage_bytes) { return (196608 / stage_bytes) < 8 ? (196608 / stage_bytes) : 8; }
+
+template <int PREC, int ROW_BYTES, int METRIC, bool VEC, bool CTA2>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
           const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
           float* __restrict__ out, int64_t ld_out,
           float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric) {
   using C = Pipe<PREC, ROW_BYTES>;
-  constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN * ROW_BYTES;
-  constexpr int STAGE_BYTES = C::PLANES * A_PLANE + C::PLANES_B * B_PLANE;
+  constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;            // gallery rows THIS CTA stages per k-block
+  constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN_LOCAL * ROW_BYTES;
+  constexpr int STAGE_BYTES = C::PLANES * A_PLANE + C::PLANES_B * B_PLANE;   // per CTA
+  constexpr int NSTAGES = CTA2 ? pair_stages(STAGE_BYTES) : C::STAGES;
   constexpr int K_PER_BLOCK = ROW_BYTES / C::ELEM;       // elements of K per stage
   constexpr int K_STEPS = K_PER_BLOCK / C::UMMA_K;       // 4
-  constexpr uint32_t IDESC = make_idesc(C::FMT, BM, BN);
+  constexpr uint32_t IDESC = make_idesc(C::FMT, CTA2 ? 2 * BM : BM, BN);
   constexpr bool kScaled = PREC == MPREID_3XFP16 || PREC == MPREID_2XFP16;   // operands carry per-row 2^s scales
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-B aligned tiles
-  const uint32_t bar_base = base + C::STAGES * STAGE_BYTES;
+  const uint32_t bar_base = base + NSTAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 4);
   const uint32_t gvec_base = bar_base + 256u;              // 2 x 256 float2: per-column (aux, scale) of the tile
   const uint32_t stage_base = gvec_base + 2u * BN * 8u;    // 4 warps x 4 KB output staging
+  // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers); the pair takes the
+  // tiles (2p, 2p+1) of the band-major order, which are vertically adjacent (band heights are even)
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  const int tile_first = CTA2 ? (int)((blockIdx.x >> 1) << 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x & ~1u) : (int)gridDim.x;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int total_tiles = symmetric ? sym_total_tiles(m_blocks, n_blocks) : m_blocks * n_blocks;
+  // CTA pairs count tiles in units of one CTA (two per pair tile) so that the loops below are shared
+  const int total_tiles = symmetric ? (CTA2 ? 2 * sym_pair_total(m_blocks >> 1) : sym_total_tiles(m_blocks, n_blocks)) : m_blocks * n_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.b_hi);
@@ -257,15 +364,15 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+      for (int s = 0; s < NSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CTA2 ? 8 : 4); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    if (CTA2) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // the peer's barriers must exist before anything targets them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -274,28 +381,39 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         // symmetric mode: tiles below the diagonal block column are never visited, the mirrors fill them
-        const TileCoord t = symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
+        const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          const int kc = kb * K_PER_BLOCK;
-          tma_load_2d(sa, &maps.a_hi, full_bar(stage), kc, t.m_blk * BM);
-          if (C::PLANES == 2) tma_load_2d(sa + A_PLANE, &maps.a_lo, full_bar(stage), kc, t.m_blk * BM);
           const uint32_t sb = sa + C::PLANES * A_PLANE;
-          tma_load_2d(sb, &maps.b_hi, full_bar(stage), kc, t.n_blk * BN);
-          if (C::PLANES_B == 2) tma_load_2d(sb + B_PLANE, &maps.b_lo, full_bar(stage), kc, t.n_blk * BN);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          const int kc = kb * K_PER_BLOCK;
+          if (CTA2) {
+            // both CTAs' bytes are counted on the leader's barrier (armed by the leader alone)
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            const uint32_t lbar = map_to_cta(full_bar(stage), 0u);
+            tma_load_2d_pair(sa, &maps.a_hi, lbar, kc, t.m_blk * BM);
+            if (C::PLANES == 2) tma_load_2d_pair(sa + A_PLANE, &maps.a_lo, lbar, kc, t.m_blk * BM);
+            const int brow = t.n_blk * BN + (int)cta_rank * BN_LOCAL;
+            tma_load_2d_pair(sb, &maps.b_hi, lbar, kc, brow);
+            if (C::PLANES_B == 2) tma_load_2d_pair(sb + B_PLANE, &maps.b_lo, lbar, kc, brow);
+          } else {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sa, &maps.a_hi, full_bar(stage), kc, t.m_blk * BM);
+            if (C::PLANES == 2) tma_load_2d(sa + A_PLANE, &maps.a_lo, full_bar(stage), kc, t.m_blk * BM);
+            tma_load_2d(sb, &maps.b_hi, full_bar(stage), kc, t.n_blk * BN);
+            if (C::PLANES_B == 2) tma_load_2d(sb + B_PLANE, &maps.b_lo, full_bar(stage), kc, t.n_blk * BN);
+          }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+    // ================================ MMA issuer (CTA pair: the leader only) ================================
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       ++it;
@@ -309,28 +427,37 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint32_t sb = sa + C::PLANES * A_PLANE;
           const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sa), b_hi = make_smem_desc<ROW_BYTES>(sb);
+          auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+            if (CTA2) umma_pair<PREC>(tmem_d, ad, bd, IDESC, acc); else umma<PREC>(tmem_d, ad, bd, IDESC, acc);
+          };
 #pragma unroll
           for (int k = 0; k < K_STEPS; ++k) {
             const uint64_t koff = (uint64_t)((k * C::UMMA_K * C::ELEM) >> 4);  // +32 B per k-step inside the atom
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             if (C::PLANES == 2 && C::PLANES_B == 2) {
               const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sa + A_PLANE), b_lo = make_smem_desc<ROW_BYTES>(sb + B_PLANE);
-              umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
-              umma<PREC>(tmem_d, a_hi + koff, b_lo + koff, IDESC, 1u);
-              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
+              mma(a_lo + koff, b_hi + koff, acc);
+              mma(a_hi + koff, b_lo + koff, 1u);
+              mma(a_hi + koff, b_hi + koff, 1u);
             } else if (C::PLANES == 2) {
               const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sa + A_PLANE);
-              umma<PREC>(tmem_d, a_lo + koff, b_hi + koff, IDESC, acc);
-              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, 1u);
+              mma(a_lo + koff, b_hi + koff, acc);
+              mma(a_hi + koff, b_hi + koff, 1u);
             } else {
-              umma<PREC>(tmem_d, a_hi + koff, b_hi + koff, IDESC, acc);
+              mma(a_hi + koff, b_hi + koff, acc);
             }
           }
-          umma_commit(empty_bar(stage));                       // smem slot reusable once these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          // smem slot reusable (in both CTAs) once these MMAs retire; accumulator complete after the last k-block
+          if (CTA2) {
+            umma_commit_pair(empty_bar(stage));
+            if (kb == num_k_blocks - 1) umma_commit_pair(tfull_bar(as));
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == num_k_blocks - 1) umma_commit(tfull_bar(as));
+          }
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -344,8 +471,8 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 1024;
     float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric);
       // symmetric (all-pairs) mode: a tile strictly right of the diagonal block column also writes its
       // transpose, which is exactly the set of tiles skipped above; diagonal tiles (n == m/2) do not
       const bool mirror = symmetric && t.n_blk > (t.m_blk >> 1);
@@ -447,13 +574,21 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0u));   // the leader's MMA warp waits for all 8 epilogue warps
+        else mbar_arrive(tempty_bar(as));
+      }
       if (row_max && row_ok && rmax > -INFINITY) atomic_max_f32(&row_max[gm], rmax);
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CTA2) {
+    cluster_sync_all();   // neither CTA may leave while the other can still touch its barriers / shared memory
+    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -487,32 +622,37 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, 
   return MPREID_OK;
 }
 
-template <int PREC, int ROW_BYTES>
+template <int PREC, int ROW_BYTES, bool CTA2>
 static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                   const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max,
                   int symmetric, cudaStream_t st) {
   using C = Cfg<PREC>;
   constexpr int kpb = ROW_BYTES / C::ELEM;
+  constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;
   MPREID_REQUIRE(ldk % kpb == 0, "dist_tc: operand planes must be padded to a multiple of %d elements (got %lld)", kpb, (long long)ldk);
   MPREID_REQUIRE(((uintptr_t)qa & 15) == 0 && ((uintptr_t)ga & 15) == 0, "dist_tc: operands must be 16-byte aligned");
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
   if ((rc = make_map(&maps.a_hi, qa, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
-  if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
+  if ((rc = make_map(&maps.b_hi, ga, G, ldk, C::ELEM, BN_LOCAL, ROW_BYTES)) != MPREID_OK) return rc;
   if (C::PLANES == 2 && (rc = make_map(&maps.a_lo, qb, Q, ldk, C::ELEM, BM, ROW_BYTES)) != MPREID_OK) return rc;
-  if (PlanesB<PREC>::value == 2 && (rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN, ROW_BYTES)) != MPREID_OK) return rc;
-  const int m_blocks = (int)ceil_div(Q, BM), n_blocks = (int)ceil_div(G, BN);
+  if (PlanesB<PREC>::value == 2 && (rc = make_map(&maps.b_lo, gb, G, ldk, C::ELEM, BN_LOCAL, ROW_BYTES)) != MPREID_OK) return rc;
+  int m_blocks = (int)ceil_div(Q, BM);
+  if (CTA2) m_blocks += m_blocks & 1;   // pairs take two vertically adjacent 128-row blocks; a padding block is all out of range
+  const int n_blocks = (int)ceil_div(G, BN);
   MPREID_REQUIRE((int64_t)m_blocks * n_blocks < INT32_MAX, "dist_tc: too many tiles");
-  const int64_t total = symmetric ? sym_total_tiles(m_blocks, n_blocks) : (int64_t)m_blocks * n_blocks;
+  const int64_t total = symmetric ? (CTA2 ? 2 * (int64_t)sym_pair_total(m_blocks >> 1) : sym_total_tiles(m_blocks, n_blocks)) : (int64_t)m_blocks * n_blocks;
   const int sms = sm_count_of_current_device();
-  const int grid = (int)(total < sms ? total : sms);
-  constexpr int STAGE_BYTES = (C::PLANES * BM + PlanesB<PREC>::value * BN) * ROW_BYTES;
-  const int smem = C::STAGES * (128 / ROW_BYTES) * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
+  int grid = (int)(total < sms ? total : sms);
+  if (CTA2) grid &= ~1;
+  constexpr int STAGE_BYTES = (C::PLANES * BM + PlanesB<PREC>::value * BN_LOCAL) * ROW_BYTES;
+  constexpr int NSTAGES = CTA2 ? pair_stages(STAGE_BYTES) : C::STAGES * (128 / ROW_BYTES);
+  const int smem = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
   const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true>);   // no casts: a signature mismatch must not compile
+  using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true, CTA2>);   // no casts: a signature mismatch must not compile
   KernT kern = nullptr;
-#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, M, true> : &k_dist_tc<PREC, ROW_BYTES, M, false>
+#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, M, true, CTA2> : &k_dist_tc<PREC, ROW_BYTES, M, false, CTA2>
   switch (metric) {
     case MPREID_SQEUCLID: MPREID_PICK(MPREID_SQEUCLID); break;
     case MPREID_ARCCOS: MPREID_PICK(MPREID_ARCCOS); break;
@@ -521,8 +661,22 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   }
 #undef MPREID_PICK
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, (int)Q, (int)G, (int)(ldk / kpb), out, ld_out, row_max,
-                                    m_blocks, n_blocks, symmetric);
+  const int nkb = (int)(ldk / kpb);
+  const int Qi = (int)Q, Gi = (int)G;
+  if (CTA2) {
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MPREID_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max,
+                                         m_blocks, n_blocks, symmetric));
+  } else {
+    kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max, m_blocks, n_blocks, symmetric);
+  }
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }
@@ -542,10 +696,17 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
   // pipeline shape: 128-byte smem rows (128B swizzle).  A 64-byte-row / twice-as-deep variant (template parameter
   // ROW_BYTES = 64) was measured 7 % slower at MSMT17 shape (6.18 vs 5.78 ms) and is not instantiated.
 #define MPREID_ARGS qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st
-  if (precision == MPREID_3XTF32) return tc::launch<MPREID_3XTF32, 128>(MPREID_ARGS);
-  if (precision == MPREID_3XFP16) return tc::launch<MPREID_3XFP16, 128>(MPREID_ARGS);
-  if (precision == MPREID_2XFP16) return tc::launch<MPREID_2XFP16, 128>(MPREID_ARGS);
-  return tc::launch<MPREID_BF16, 128>(MPREID_ARGS);
+  // CTA pairs (cta_group::2, 256x256 tile per pair, 3 x 64 KB stages per CTA) for the rectangular GEMM of the
+  // split-fp16 modes (rectangular and symmetric all-pairs); MPREID_GEMM_PAIR=0 selects the single-CTA kernel.
+  const char* pair_env = getenv("MPREID_GEMM_PAIR");   // read per call: tests flip it inside one process
+  const bool pair_ok = !(pair_env && pair_env[0] == '0');
+  // symmetric all-pairs launches are long enough to sit at the power cap either way; the pair kernel measured 3 %
+  // slower there (46.7 vs 45.0 ms for the MSMT17 re-ranking pass), so it is used only on request (MPREID_GEMM_PAIR=2)
+  const bool pair = pair_ok && Q > tc::BM && (!symmetric || (pair_env && pair_env[0] == '2'));
+  if (precision == MPREID_3XTF32) return tc::launch<MPREID_3XTF32, 128, false>(MPREID_ARGS);
+  if (precision == MPREID_3XFP16) return pair ? tc::launch<MPREID_3XFP16, 128, true>(MPREID_ARGS) : tc::launch<MPREID_3XFP16, 128, false>(MPREID_ARGS);
+  if (precision == MPREID_2XFP16) return pair ? tc::launch<MPREID_2XFP16, 128, true>(MPREID_ARGS) : tc::launch<MPREID_2XFP16, 128, false>(MPREID_ARGS);
+  return tc::launch<MPREID_BF16, 128, false>(MPREID_ARGS);
 #undef MPREID_ARGS
 }
 

@@ -110,6 +110,27 @@ def test_tcgen05_matches_simt_on_ragged_tiles():
             assert torch.equal(rm, d.max(dim=1).values), (Q, G, D, prec)
 
 
+def test_cta_pair_gemm_bit_identical_to_single_cta(monkeypatch):
+    """The cta_group::2 kernel (two CTAs share a 256 x 256 tile) accumulates every output in the same order
+    as the single-CTA kernel: results and fused row maxima must match bit for bit, odd block counts included."""
+    torch.manual_seed(3)
+    for (Q, G, D) in [(129, 300, 64), (300, 1000, 128), (641, 5000, 1280), (2049, 777, 200), (3000, 9000, 768)]:
+        x = torch.randn(Q + G, D, device=DEV)
+        for prec in ("3xfp16", "2xfp16"):
+            p = E.prep_rows(x, True, prec)
+            q, g = p.rows(0, Q), p.rows(Q, Q + G)
+            for metric in ("sqeuclid", "arccos", "one_minus_dot", "sqrt_euclid"):
+                res = {}
+                for mode in ("0", "1"):
+                    monkeypatch.setenv("MPREID_GEMM_PAIR", mode)
+                    rm = torch.empty(Q, device=DEV)
+                    res[mode] = (E.dist_matrix(q, g, metric, prec, row_max=rm), rm)
+                torch.cuda.synchronize()
+                assert torch.equal(res["0"][0], res["1"][0]), (Q, G, D, prec, metric)
+                assert torch.equal(res["0"][1], res["1"][1]), (Q, G, D, prec, metric)
+                assert torch.equal(res["1"][1], res["1"][0].max(dim=1).values)
+
+
 # ------------------------------------------------------------------------------------ rank + CMC/AP
 @pytest.mark.parametrize("name", CASES)
 def test_rank_eval_bit_exact_on_reference_distmat(golden_dir, name):
@@ -421,6 +442,23 @@ def test_all_pairs_symmetric_mode(prec):
             blk = (torch.arange(N, device=DEV)[None, :] // 256) >= (torch.arange(N, device=DEV)[:, None] // 256)
             assert torch.equal(d[blk], plain[blk]), (prec, N)
         assert torch.equal(rm, d.max(dim=1).values), (prec, N)
+
+
+def test_all_pairs_symmetric_cta_pair_variant(monkeypatch):
+    """MPREID_GEMM_PAIR=2 runs the symmetric all-pairs GEMM on CTA pairs (square 256 x 256 pair tiles): same
+    mirrored / diagonal structure, so the result is bit-identical to the single-CTA symmetric kernel."""
+    torch.manual_seed(4)
+    for N, D in [(130, 100), (700, 256), (2500, 320), (5000, 128)]:
+        x = torch.randn(N, D, device=DEV)
+        p = E.prep_rows(x, True, "3xfp16")
+        res = {}
+        for mode in ("0", "2"):
+            monkeypatch.setenv("MPREID_GEMM_PAIR", mode)
+            rm = torch.empty(N, device=DEV)
+            res[mode] = (E.dist_matrix_all_pairs(p, "3xfp16", row_max=rm), rm)
+        torch.cuda.synchronize()
+        assert torch.equal(res["0"][0], res["2"][0]), N
+        assert torch.equal(res["0"][1], res["2"][1]), N
 
 
 # ------------------------------------------------------------------------------------ the other BASELINE configs at full shape
