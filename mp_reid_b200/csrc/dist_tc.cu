@@ -537,7 +537,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
               if (grow < Q) {
                 float* dst = out + (int64_t)grow * ld_out + gcol;
                 if (VEC && gcol + 4 <= G) {
-                  *reinterpret_cast<float4*>(dst) = v;
+                  __stcs(reinterpret_cast<float4*>(dst), v);   // streaming: the matrix must not evict the operand band from L2
                 } else {
                   if (gcol < G) dst[0] = v.x;
                   if (gcol + 1 < G) dst[1] = v.y;
@@ -551,7 +551,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
               // transpose: for a fixed column the 32 lanes hold 32 consecutive rows -> one 128-byte store
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (row_ok && gn0 + j < G) out[(int64_t)(gn0 + j) * ld_out + gm] = d[j];
+                if (row_ok && gn0 + j < G) __stcs(out + (int64_t)(gn0 + j) * ld_out + gm, d[j]);
               if (row_max) {
                 // column maxima (the row maxima of the mirrored block): butterfly transpose-reduce, 31 shuffles
 #pragma unroll
