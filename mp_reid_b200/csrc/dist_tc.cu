@@ -8,6 +8,8 @@
 //   3xTF32  the fp32 operands are pre-split (prep.cu) into TF32-exact planes  x = hi + lo;  the
 //           accumulator receives  lo*hi + hi*lo + hi*hi  (error ~2^-21 relative per product, i.e.
 //           fp32-level; the lo*lo term is below fp32 rounding).  Three kind::tf32 MMAs per k-step.
+//   3xFP16  (default) the same split on per-row power-of-two scaled fp16 planes: twice the MMA rate.
+//   2xFP16  stated fast mode: the gallery side contributes only its hi plane (two MMAs per k-step).
 //   BF16    bf16-rounded operands, one kind::f16 MMA per k-step, fp32 accumulate.
 //
 // Kernel shape: persistent, one CTA per SM, 192 threads = 6 warps
@@ -20,6 +22,13 @@
 //               row per thread.
 // Tiles are visited band-major (16 m-blocks per band, m fastest) so the query band stays in L2 and
 // every gallery tile is fetched from HBM once per band.
+//
+// CTA-pair variant (template parameter CTA2, rectangular launches of the split-fp16 modes): clusters of two
+// CTAs on one TPC share a 256x256 tile through tcgen05.mma.cta_group::2.  Each CTA stages its own 128
+// query rows and half of the gallery rows (64 KB per k-block -> three stages), the leader CTA issues the
+// MMAs and multicast-commits to the barriers of both CTAs; each CTA's epilogue warps read their own 128
+// accumulator lanes.  Per output element the accumulation order is the single-CTA one: results are
+// bit-identical (tests/test_gpu_parity.py::test_cta_pair_gemm_bit_identical_to_single_cta).
 #include <cuda.h>
 #include <cstdlib>
 
