@@ -185,6 +185,21 @@ def clipstyle_eval(distmat, q_pids, g_pids, q_camids, g_camids):
     return _eval_device(d, q_pids, g_pids, q_camids, g_camids, min(50, d.shape[1]), "pid_cam", "all")
 
 
+def _merge_adjacent(views):
+    """Row views that follow each other in the same allocation (the pieces of one upload) -> one view."""
+    out = []
+    for v in views:
+        if out:
+            a = out[-1]
+            if (v.dim() == 2 and a.stride() == v.stride() and v.stride(1) == 1 and v.stride(0) == v.shape[1]
+                    and a.untyped_storage().data_ptr() == v.untyped_storage().data_ptr()
+                    and a.storage_offset() + a.numel() == v.storage_offset()):
+                out[-1] = torch.as_strided(a, (a.shape[0] + v.shape[0], a.shape[1]), a.stride(), a.storage_offset())
+                continue
+        out.append(v)
+    return out
+
+
 class R1_mAP_eval():
     """utils/metrics.py:91-134.  Features stay on the GPU between update() and compute().
 
@@ -222,13 +237,22 @@ class R1_mAP_eval():
             feats.append(feat.to(dev, dtype=torch.float32))
             self._events.append(None)
         else:
+            # upload on the side stream in pieces of <= MPREID_COPY_ROWS rows, one event each: compute() starts the
+            # GEMM of a piece as soon as it has landed, so what is left after the final copy is one small chunk
             cs = _copy_stream(dev)
+            piece = max(32, int(os.environ.get("MPREID_COPY_ROWS", "2048")))
+            if feat.dtype != torch.float32:
+                feat = feat.float()
+            n = feat.shape[0]
             with torch.cuda.stream(cs):
-                t = feat.to(dev, dtype=torch.float32, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            feats.append(t)
-            self._events.append(ev)
+                t = torch.empty(feat.shape, dtype=torch.float32, device=dev)
+                for s0 in range(0, n, piece):
+                    s1 = min(n, s0 + piece)
+                    t[s0:s1].copy_(feat[s0:s1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    feats.append(t[s0:s1])
+                    self._events.append(ev)
         self.pids.extend(pid)
         self.camids.extend(camid)
 
@@ -274,25 +298,21 @@ class R1_mAP_eval():
             print('=> Computing DistMat with euclidean_distance')
             q_parts, g_parts = self._split_rows()
             num_g = sum(t.shape[0] for _, t in g_parts)
+            # (labels are uploaded by _eval_device AFTER the GEMMs: an early host->device copy on this stream would
+            #  queue behind every feature piece on the copy engine and stall the whole pipeline)
             self._wait(0, (q_parts[-1][0] + 1) if q_parts else 0)
             q = E.prep_rows(torch.cat([t for _, t in q_parts], dim=0) if len(q_parts) != 1 else q_parts[0][1],
                             normalize=norm, precision=self._precision, keep_xn=True)
             dist = E.alloc_dist(nq, num_g, q.sqnorm.device)
             chunk_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32)
-            # gallery chunks of chunk_rows rows, cut at multiples of 32 rows so that every column block of
-            # the distance matrix starts 128-byte aligned (vector stores); batches are split by view.  The
-            # last chunks halve down to ~1k rows: the GEMM of a chunk can only start when its last row has
-            # arrived, so the size of the final chunk is what is left to do after the last host->device copy.
-            sizes, rem = [], num_g
-            while rem > 0:
-                sz = chunk_rows if rem > 2 * chunk_rows else max(min(1024, chunk_rows), (rem // 2) // 32 * 32)
-                if rem - sz < 512:
-                    sz = rem
-                sizes.append(sz)
-                rem -= sz
+            tail_rows = min(chunk_rows, 2048)
+            # gallery chunks: whatever has landed is contracted once it amounts to chunk_rows rows (tail_rows for
+            # the last 2 * chunk_rows rows: the GEMM of a chunk can only start when its last row has arrived, so
+            # the final chunk is what is left to do after the last host->device copy); cuts at multiples of 32
+            # rows so that every column block of the distance matrix starts 128-byte aligned (vector stores)
             gf = torch.empty((num_g, q.D), dtype=torch.float32, device=q.sqnorm.device)   # normalised gallery rows (returned)
             off = 0
-            pend, pend_rows, last_bi, si = [], 0, -1, 0
+            pend, pend_rows, last_bi, arrived = [], 0, -1, 0
 
             def flush(rows_out):
                 nonlocal pend, pend_rows, off
@@ -304,6 +324,7 @@ class R1_mAP_eval():
                         take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
                     else:
                         rest.append(t)
+                take = _merge_adjacent(take)   # pieces of one upload are neighbouring views: no copy
                 blk = take[0] if len(take) == 1 else torch.cat(take, dim=0)
                 g = E.prep_rows(blk, normalize=norm, precision=self._precision, xn_out=gf[off:off + rows_out])
                 E.dist_matrix(q, g, self._metric, self._precision, out=dist[:, off:off + rows_out])
@@ -314,9 +335,12 @@ class R1_mAP_eval():
                 self._wait(last_bi + 1, bi + 1)
                 last_bi = bi
                 pend.append(t); pend_rows += t.shape[0]
-                while si < len(sizes) and pend_rows >= sizes[si]:
-                    flush(sizes[si])
-                    si += 1
+                arrived += t.shape[0]
+                left = num_g - arrived
+                if left == 0:
+                    flush(pend_rows)
+                elif pend_rows >= (chunk_rows if left > 2 * chunk_rows else tail_rows):
+                    flush(pend_rows // 32 * 32)
             qf = q.xn
         cmc, mAP = _eval_device(dist, q_pids, g_pids, q_camids, g_camids, 50, self._junk)  # :132 (max_rank is not forwarded)
         return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, qf, gf
