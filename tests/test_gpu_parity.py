@@ -286,6 +286,28 @@ def test_evaluator_drop_in_sequence(golden_dir, name, capsys):
     assert np.array_equal(cmc2, g["ref_stable_cmc"]) and mAP2 == g["ref_stable_mAP"]
 
 
+def test_evaluator_batching_invariance(monkeypatch):
+    """Ragged host batches, small upload pieces and small GEMM chunks give the same matrix, bit for bit, as one
+    device-resident batch (every distance depends on its own two rows only)."""
+    rng = np.random.RandomState(11)
+    Q, G, D = 300, 7001, 256
+    x = torch.from_numpy(rng.randn(Q + G, D).astype(np.float32))
+    pid = rng.randint(0, 60, Q + G); cam = rng.randint(0, 6, Q + G)
+    ev = metrics.R1_mAP_eval(Q); ev.reset()
+    ev.update((x.to(DEV), pid, cam))
+    cmc0, mAP0, d0, *_, qf0, gf0 = ev.compute()
+    monkeypatch.setenv("MPREID_CHUNK_ROWS", "1024")
+    monkeypatch.setenv("MPREID_COPY_ROWS", "500")
+    ev = metrics.R1_mAP_eval(Q); ev.reset()
+    s = 0
+    for n in [1000, 37, 4100, 5, 1, 2000, 158]:      # sums to Q + G; the query / gallery cut falls inside a batch
+        ev.update((x[s:s + n].pin_memory() if n % 2 else x[s:s + n], pid[s:s + n], cam[s:s + n])); s += n
+    assert s == Q + G
+    cmc1, mAP1, d1, *_, qf1, gf1 = ev.compute()
+    assert np.array_equal(np.asarray(d0), np.asarray(d1)) and np.array_equal(cmc0, cmc1) and mAP0 == mAP1
+    assert torch.equal(qf0, qf1) and torch.equal(gf0, gf1)
+
+
 def test_evaluator_reranking_flag(golden_dir, capsys):
     g = load(golden_dir, "rerank_small")
     ev = metrics.R1_mAP_eval(len(g["qf"]), reranking=True)
