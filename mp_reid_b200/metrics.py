@@ -27,7 +27,29 @@ def _device():
     return torch.device(os.environ.get("MPREID_DEVICE", f"cuda:{torch.cuda.current_device()}"))
 
 
+def _devices():
+    """Devices of the single-process multi-GPU mode: MPREID_DEVICES="0,1,2" or "all" (default: the one device).
+    The first entry is where update() uploads; the evaluator is driven from ONE host thread, as the reference's
+    do_inference is (under DIST_TRAIN only rank 0 evaluates, processor/processor.py:117-118)."""
+    spec = os.environ.get("MPREID_DEVICES", "").strip().lower()
+    d0 = _device()
+    if not spec:
+        return [d0]
+    ids = list(range(torch.cuda.device_count())) if spec == "all" else [int(x) for x in spec.split(",") if x.strip() != ""]
+    devs = [d0] + [torch.device(f"cuda:{i}") for i in ids if i != d0.index]
+    return devs
+
+
 _COPY_STREAMS = {}
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, tag):
+    """Long-lived auxiliary streams (peer-to-peer fan-out / receive), one per (device, purpose)."""
+    key = (dev.index, tag)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 def _copy_stream(dev):
@@ -125,6 +147,33 @@ class LazyDistmat:
 
     def __repr__(self):
         return f"LazyDistmat(shape={self.shape}, device={self._dev.device})"
+
+
+class LazyDistmatShards(LazyDistmat):
+    """The same handle over query-row shards that live on several devices (single-process multi-GPU mode)."""
+
+    def __init__(self, shards):
+        self._shards = list(shards)
+        self._dev = None
+        self._host = None
+        self.shape = (sum(t.shape[0] for t in self._shards), self._shards[0].shape[1])
+        self.dtype = np.dtype(np.float32)
+        self.ndim = 2
+
+    @property
+    def device_tensor(self) -> torch.Tensor:
+        if self._dev is None:
+            d0 = self._shards[0].device
+            self._dev = torch.cat([t.to(d0) for t in self._shards], dim=0)
+        return self._dev
+
+    def numpy(self) -> np.ndarray:
+        if self._host is None:
+            self._host = np.concatenate([t.cpu().numpy() for t in self._shards], axis=0)
+        return self._host
+
+    def __repr__(self):
+        return f"LazyDistmatShards(shape={self.shape}, devices={[str(t.device) for t in self._shards]})"
 
 
 def _distance(qf, gf, metric, precision=None, to_host=True):
@@ -296,6 +345,9 @@ class R1_mAP_eval():
             qf, gf = q.xn, g.xn
         else:
             print('=> Computing DistMat with euclidean_distance')
+            devs = _devices()
+            if len(devs) > 1 and nq >= len(devs):
+                return self._compute_multi(devs, q_pids, g_pids, q_camids, g_camids, norm)
             q_parts, g_parts = self._split_rows()
             num_g = sum(t.shape[0] for _, t in g_parts)
             # (labels are uploaded by _eval_device AFTER the GEMMs: an early host->device copy on this stream would
@@ -344,3 +396,90 @@ class R1_mAP_eval():
             qf = q.xn
         cmc, mAP = _eval_device(dist, q_pids, g_pids, q_camids, g_camids, 50, self._junk)  # :132 (max_rank is not forwarded)
         return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, qf, gf
+
+    def _compute_multi(self, devs, q_pids, g_pids, q_camids, g_camids, norm):
+        """Single-process multi-GPU evaluation: query rows are sharded over `devs`, every gallery
+        piece is fanned out from the upload device over NVLink as soon as it has landed, each device runs the same
+        prep -> GEMM -> rank pipeline on its shard, and the per-query results are reduced by numpy on the host in
+        query order -- bit-identical to the one-device result."""
+        from .distributed import shard_bounds
+        nq, P, d0 = self.num_query, len(devs), devs[0]
+        q_parts, g_parts = self._split_rows()
+        num_g = sum(t.shape[0] for _, t in g_parts)
+        D = (q_parts[0][1] if q_parts else g_parts[0][1]).shape[1]
+        bounds = [shard_bounds(nq, P, k) for k in range(P)]
+        self._wait(0, (q_parts[-1][0] + 1) if q_parts else 0)
+        qcat = _merge_adjacent([t for _, t in q_parts])
+        qcat = qcat[0] if len(qcat) == 1 else torch.cat(qcat, dim=0)
+        q, dist, qn = [], [], []
+        for k, dev in enumerate(devs):
+            lo, hi = bounds[k]
+            with torch.cuda.device(dev):
+                xq = qcat[lo:hi] if k == 0 else qcat[lo:hi].to(dev, non_blocking=True)
+                q.append(E.prep_rows(xq, normalize=norm, precision=self._precision, keep_xn=True))
+                dist.append(E.alloc_dist(hi - lo, num_g, dev))
+        gf = torch.empty((num_g, D), dtype=torch.float32, device=d0)   # normalised gallery rows (returned)
+        # fewer, larger chunks than on one device: every flush costs host time once per device
+        chunk_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32) * min(P, 4)
+        tail_rows = min(chunk_rows, 4096)
+        pend, pend_rows, off, arrived, last_bi = [], 0, 0, 0, -1
+        main0 = torch.cuda.current_stream(d0)
+
+        def flush(rows_out):
+            # the chunk is assembled on device 0, fanned out peer-to-peer (one copy per peer, on its own source-side
+            # stream so the NVLink transfers overlap each other and device 0's GEMM), then contracted everywhere
+            nonlocal pend, pend_rows, off
+            take, got, rest = [], 0, []
+            for t in pend:
+                if got + t.shape[0] <= rows_out:
+                    take.append(t); got += t.shape[0]
+                elif got < rows_out:
+                    take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
+                else:
+                    rest.append(t)
+            take = _merge_adjacent(take)
+            blk0 = take[0] if len(take) == 1 else torch.cat(take, dim=0)
+            blks = [blk0]
+            for k in range(1, P):
+                tx = _side_stream(d0, ("tx", k))
+                tx.wait_stream(main0)
+                with torch.cuda.stream(tx):
+                    blks.append(blk0.to(devs[k], non_blocking=True))   # the peer's current stream waits for the copy
+                blk0.record_stream(tx)
+            for k, dev in enumerate(devs):
+                with torch.cuda.device(dev):
+                    g = E.prep_rows(blks[k], normalize=norm, precision=self._precision, keep_xn=False,
+                                    xn_out=gf[off:off + rows_out] if k == 0 else None)
+                    E.dist_matrix(q[k], g, self._metric, self._precision, out=dist[k][:, off:off + rows_out])
+            off += rows_out
+            pend, pend_rows = rest, pend_rows - rows_out
+
+        for bi, t in g_parts:
+            self._wait(last_bi + 1, bi + 1)
+            last_bi = bi
+            pend.append(t); pend_rows += t.shape[0]; arrived += t.shape[0]
+            left = num_g - arrived
+            if left == 0:
+                flush(pend_rows)
+            elif pend_rows >= (chunk_rows if left > 2 * chunk_rows else tail_rows):
+                flush(pend_rows // 32 * 32)
+        # rank / AP per shard, then ONE host-side reduction in query order
+        results = []
+        for k, dev in enumerate(devs):
+            lo, hi = bounds[k]
+            results.append(E.rank_eval_async(dist[k], q_pids[lo:hi], g_pids, q_camids[lo:hi], g_camids, self._junk))
+        fh, ap, nr = [], [], []
+        for k, dev in enumerate(devs):
+            lo, hi = bounds[k]
+            with torch.cuda.device(dev):
+                a, b, c, st = results[k].to_host()
+                if int(st[0]) != 0:   # positives workspace too small on this shard: exact re-run
+                    a, b, c = E.rank_eval_host(dist[k], q_pids[lo:hi], g_pids, q_camids[lo:hi], g_camids, self._junk)
+            fh.append(a); ap.append(b); nr.append(c)
+        max_rank = 50
+        if num_g < max_rank:
+            max_rank = num_g
+            print("Note: number of gallery samples is quite small, got {}".format(num_g))
+        cmc, mAP = E.reduce_cmc_map(np.concatenate(fh), np.concatenate(ap), np.concatenate(nr), max_rank, num_g)
+        qf = torch.cat([q[k].xn.to(d0) for k in range(P)], dim=0)
+        return cmc, mAP, LazyDistmatShards(dist), self.pids, self.camids, qf, gf

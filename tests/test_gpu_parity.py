@@ -308,6 +308,36 @@ def test_evaluator_batching_invariance(monkeypatch):
     assert torch.equal(qf0, qf1) and torch.equal(gf0, gf1)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_single_process_multi_gpu_evaluator(monkeypatch):
+    """MPREID_DEVICES: one host thread drives all GPUs (query rows sharded, gallery chunks fanned out peer to
+    peer); everything the evaluator returns equals the one-GPU result bit for bit."""
+    rng = np.random.RandomState(12)
+    Q, G, D = 1003, 20011, 256
+    x = torch.from_numpy(rng.randn(Q + G, D).astype(np.float32)).pin_memory()
+    pid = rng.randint(0, 150, Q + G); cam = rng.randint(0, 6, Q + G)
+
+    def run():
+        ev = metrics.R1_mAP_eval(Q); ev.reset()
+        for s in range(0, Q + G, 3000):
+            ev.update((x[s:s + 3000], pid[s:s + 3000], cam[s:s + 3000]))
+        return ev.compute()
+
+    monkeypatch.setenv("MPREID_CHUNK_ROWS", "2048")
+    cmc0, mAP0, d0, *_, qf0, gf0 = run()
+    monkeypatch.setenv("MPREID_DEVICES", "all")
+    for junk in ("none", "pid_cam"):
+        monkeypatch.setenv("MPREID_JUNK", junk)
+        cmc1, mAP1, d1, p1, c1, qf1, gf1 = run()
+        if junk == "none":
+            assert np.array_equal(cmc0, cmc1) and mAP0 == mAP1
+        else:
+            cmcj, mAPj = metrics.eval_func(d0, pid[:Q], pid[Q:], cam[:Q], cam[Q:], junk="pid_cam")
+            assert np.array_equal(cmcj, cmc1) and mAPj == mAP1
+        assert d1.shape == (Q, G) and np.array_equal(np.asarray(d0), np.asarray(d1))
+        assert torch.equal(qf0, qf1) and torch.equal(gf0, gf1) and len(p1) == Q + G
+
+
 def test_evaluator_reranking_flag(golden_dir, capsys):
     g = load(golden_dir, "rerank_small")
     ev = metrics.R1_mAP_eval(len(g["qf"]), reranking=True)
