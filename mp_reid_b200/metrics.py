@@ -234,6 +234,18 @@ def clipstyle_eval(distmat, q_pids, g_pids, q_camids, g_camids):
     return _eval_device(d, q_pids, g_pids, q_camids, g_camids, min(50, d.shape[1]), "pid_cam", "all")
 
 
+def _fan_out(blk0, devs):
+    """One copy of `blk0` (on devs[0]) per device: NCCL broadcast driven from this one process (torch.cuda.comm:
+    ring / tree over NVLink instead of P-1 copies out of one GPU), plain peer-to-peer copies as the fallback."""
+    if len(devs) == 1:
+        return [blk0]
+    try:
+        from torch.cuda import comm
+        return list(comm.broadcast(blk0, devices=[d.index for d in devs]))
+    except Exception:
+        return [blk0] + [blk0.to(d, non_blocking=True) for d in devs[1:]]
+
+
 def _merge_adjacent(views):
     """Row views that follow each other in the same allocation (the pieces of one upload) -> one view."""
     out = []
@@ -358,6 +370,8 @@ class R1_mAP_eval():
             dist = E.alloc_dist(nq, num_g, q.sqnorm.device)
             chunk_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32)
             tail_rows = min(chunk_rows, 2048)
+            if all(self._events[bi] is None for bi, _ in g_parts):   # input already on the device: nothing to overlap with
+                chunk_rows = tail_rows = max(num_g, 32)
             # gallery chunks: whatever has landed is contracted once it amounts to chunk_rows rows (tail_rows for
             # the last 2 * chunk_rows rows: the GEMM of a chunk can only start when its last row has arrived, so
             # the final chunk is what is left to do after the last host->device copy); cuts at multiples of 32
@@ -419,15 +433,16 @@ class R1_mAP_eval():
                 q.append(E.prep_rows(xq, normalize=norm, precision=self._precision, keep_xn=True))
                 dist.append(E.alloc_dist(hi - lo, num_g, dev))
         gf = torch.empty((num_g, D), dtype=torch.float32, device=d0)   # normalised gallery rows (returned)
-        # fewer, larger chunks than on one device: every flush costs host time once per device
-        chunk_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32) * min(P, 4)
-        tail_rows = min(chunk_rows, 4096)
+        # fewer, larger chunks than on one device (every flush costs host time once per device); input that is already
+        # on the device is contracted in one go
+        streamed = any(self._events[bi] is not None for bi, _ in g_parts)
+        base_rows = max(32, int(os.environ.get("MPREID_CHUNK_ROWS", "8192")) // 32 * 32)
+        chunk_rows = 2 * base_rows if streamed else num_g
+        tail_rows, tail_window = (min(chunk_rows, base_rows), 2 * base_rows) if streamed else (num_g, 0)
         pend, pend_rows, off, arrived, last_bi = [], 0, 0, 0, -1
-        main0 = torch.cuda.current_stream(d0)
 
         def flush(rows_out):
-            # the chunk is assembled on device 0, fanned out peer-to-peer (one copy per peer, on its own source-side
-            # stream so the NVLink transfers overlap each other and device 0's GEMM), then contracted everywhere
+            # the chunk is assembled on device 0, broadcast to the peers over NVLink, then contracted everywhere
             nonlocal pend, pend_rows, off
             take, got, rest = [], 0, []
             for t in pend:
@@ -439,13 +454,7 @@ class R1_mAP_eval():
                     rest.append(t)
             take = _merge_adjacent(take)
             blk0 = take[0] if len(take) == 1 else torch.cat(take, dim=0)
-            blks = [blk0]
-            for k in range(1, P):
-                tx = _side_stream(d0, ("tx", k))
-                tx.wait_stream(main0)
-                with torch.cuda.stream(tx):
-                    blks.append(blk0.to(devs[k], non_blocking=True))   # the peer's current stream waits for the copy
-                blk0.record_stream(tx)
+            blks = _fan_out(blk0, devs)
             for k, dev in enumerate(devs):
                 with torch.cuda.device(dev):
                     g = E.prep_rows(blks[k], normalize=norm, precision=self._precision, keep_xn=False,
@@ -461,7 +470,7 @@ class R1_mAP_eval():
             left = num_g - arrived
             if left == 0:
                 flush(pend_rows)
-            elif pend_rows >= (chunk_rows if left > 2 * chunk_rows else tail_rows):
+            elif pend_rows >= (chunk_rows if left > tail_window else tail_rows):
                 flush(pend_rows // 32 * 32)
         # rank / AP per shard, then ONE host-side reduction in query order
         results = []
