@@ -127,3 +127,19 @@ def test_evaluator_surface_matches_reference():
     ev = metrics.R1_mAP_eval(10)
     with pytest.raises(AttributeError):  # update before reset, as in the reference (lists undefined)
         ev.update((torch.zeros(2, 4), (1, 2), (0, 0)))
+
+
+def test_merge_adjacent_views_is_copy_free_and_exact():
+    """Pieces of one upload are neighbouring row views of one allocation: they merge into one view (no copy);
+    views from different allocations, gaps or reordered pieces stay separate."""
+    import torch
+    from mp_reid_b200.metrics import _merge_adjacent
+    t = torch.arange(60.).reshape(15, 4)
+    u = torch.zeros(3, 4)
+    out = _merge_adjacent([t[0:3], t[3:5], t[5:9], u, t[9:12], t[13:15], t[12:13]])
+    assert [tuple(o.shape) for o in out] == [(9, 4), (3, 4), (3, 4), (2, 4), (1, 4)]
+    assert out[0].data_ptr() == t.data_ptr() and torch.equal(out[0], t[0:9])      # a view, not a copy
+    assert torch.equal(torch.cat(out), torch.cat([t[0:9], u, t[9:12], t[13:15], t[12:13]]))
+    cols = t[:, :2]                                                                 # column slices are not contiguous rows
+    assert len(_merge_adjacent([cols[0:2], cols[2:4]])) == 2
+    assert _merge_adjacent([]) == []
