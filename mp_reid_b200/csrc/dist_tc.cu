@@ -20,8 +20,8 @@
 //   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, norm add / arccos / 1-dot, row max,
 //               store.  Warp w owns TMEM lanes 32*(w%4)..+31 (hardware restriction), i.e. one output
 //               row per thread.
-// Tiles are visited band-major (16 m-blocks per band, m fastest) so the query band stays in L2 and
-// every gallery tile is fetched from HBM once per band.
+// Tiles are visited band-major (m fastest inside a band of query blocks sized to ~24 MB of operand planes)
+// so the query band stays in L2 and every gallery tile streams past once per band.
 //
 // CTA-pair variant (template parameter CTA2, rectangular launches of the split-fp16 modes): clusters of two
 // CTAs on one TPC share a 256x256 tile through tcgen05.mma.cta_group::2.  Each CTA stages its own 128
@@ -227,14 +227,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }
 
 struct TileCoord { int m_blk, n_blk; };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int m_blocks, int n_blocks) {
-  const int band_tiles = BAND * n_blocks;
+__device__ __forceinline__ TileCoord decode_tile(int tile, int m_blocks, int n_blocks, int band = BAND) {
+  const int band_tiles = band * n_blocks;
   const int b = tile / band_tiles;
   const int rem = tile - b * band_tiles;
-  const int h = min(BAND, m_blocks - b * BAND);
+  const int h = min(band, m_blocks - b * band);
   TileCoord t;
   t.n_blk = rem / h;
-  t.m_blk = b * BAND + (rem - t.n_blk * h);
+  t.m_blk = b * band + (rem - t.n_blk * h);
   return t;
 }
 
@@ -313,9 +313,9 @@ __device__ __forceinline__ TileCoord sym_pair_decode(int pt, int Mp) {
 
 // tile -> (128-row query block, 256-column gallery block) of THIS CTA
 template <bool CTA2>
-__device__ __forceinline__ TileCoord tile_coord(int tile, int cta_rank, int m_blocks, int n_blocks, int symmetric) {
-  if (!CTA2) return symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks);
-  if (!symmetric) return decode_tile(tile + cta_rank, m_blocks, n_blocks);
+__device__ __forceinline__ TileCoord tile_coord(int tile, int cta_rank, int m_blocks, int n_blocks, int symmetric, int band) {
+  if (!CTA2) return symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks, band);
+  if (!symmetric) return decode_tile(tile + cta_rank, m_blocks, n_blocks, band);
   TileCoord t = sym_pair_decode(tile >> 1, m_blocks >> 1);
   t.m_blk = 2 * t.m_blk + cta_rank;
   return t;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
           const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
           float* __restrict__ out, int64_t ld_out,
-          float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric) {
+          float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric, int band) {
   using C = Pipe<PREC, ROW_BYTES>;
   constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;            // gallery rows THIS CTA stages per k-block
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN_LOCAL * ROW_BYTES;
@@ -392,7 +392,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       int stage = 0; uint32_t phase = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         // symmetric mode: tiles below the diagonal block column are never visited, the mirrors fill them
-        const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric);
+        const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric, band);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -402,9 +402,9 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
             // both CTAs' bytes are counted on the leader's barrier (armed by the leader alone)
             if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             const uint32_t lbar = map_to_cta(full_bar(stage), 0u);
+            const int brow = t.n_blk * BN + (int)cta_rank * BN_LOCAL;
             tma_load_2d_pair(sa, &maps.a_hi, lbar, kc, t.m_blk * BM);
             if (C::PLANES == 2) tma_load_2d_pair(sa + A_PLANE, &maps.a_lo, lbar, kc, t.m_blk * BM);
-            const int brow = t.n_blk * BN + (int)cta_rank * BN_LOCAL;
             tma_load_2d_pair(sb, &maps.b_hi, lbar, kc, brow);
             if (C::PLANES_B == 2) tma_load_2d_pair(sb + B_PLANE, &maps.b_lo, lbar, kc, brow);
           } else {
@@ -481,7 +481,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-      const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric);
+      const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric, band);
       // symmetric (all-pairs) mode: a tile strictly right of the diagonal block column also writes its
       // transpose, which is exactly the set of tiles skipped above; diagonal tiles (n == m/2) do not
       const bool mirror = symmetric && t.n_blk > (t.m_blk >> 1);
@@ -671,6 +671,17 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
 #undef MPREID_PICK
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nkb = (int)(ldk / kpb);
+  // Query-band height of the tile order (m fastest inside a band): the band's operand planes must stay L2-resident
+  // while every gallery tile streams past once per band, so fewer / taller bands mean fewer gallery re-reads.  Budget
+  // 24 MB for the band (measured at MSMT17 shape, CTA pairs: DRAM reads 6.8 GB at 16 blocks, 3.3 GB at 32, same time),
+  // balanced over the bands, even (CTA pairs take two vertically adjacent blocks).
+  const int64_t block_bytes = (int64_t)BM * ldk * C::ELEM * C::PLANES;
+  int band = (int)((24ll << 20) / (block_bytes > 0 ? block_bytes : 1));
+  band = band < BAND ? BAND : band;
+  const int n_bands = (m_blocks + band - 1) / band;
+  band = (m_blocks + n_bands - 1) / n_bands;
+  band += band & 1;
+  if (const char* band_env = getenv("MPREID_GEMM_BAND")) { const int b = atoi(band_env); if (b >= 2 && !(b & 1)) band = b; }
   const int Qi = (int)Q, Gi = (int)G;
   if (CTA2) {
     MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
@@ -682,9 +693,9 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     MPREID_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max,
-                                         m_blocks, n_blocks, symmetric));
+                                         m_blocks, n_blocks, symmetric, band));
   } else {
-    kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max, m_blocks, n_blocks, symmetric);
+    kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max, m_blocks, n_blocks, symmetric, band);
   }
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
