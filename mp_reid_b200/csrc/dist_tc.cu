@@ -240,9 +240,9 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int m_blocks, int n_b
 
 // Symmetric (all-pairs) mode visits only the tiles with n_blk >= m_blk/2 (on or right of the diagonal block
 // column), enumerated band by band in the same order as above so that the round-robin over CTAs stays balanced.
-__host__ __device__ __forceinline__ int sym_band_tiles(int b, int m_blocks, int n_blocks, int* h_out, int* jt_out) {
-  const int m0 = b * BAND;
-  const int h = (BAND < m_blocks - m0) ? BAND : (m_blocks - m0);
+__host__ __device__ __forceinline__ int sym_band_tiles(int b, int m_blocks, int n_blocks, int band, int* h_out, int* jt_out) {
+  const int m0 = b * band;
+  const int h = (band < m_blocks - m0) ? band : (m_blocks - m0);
   const int avail = n_blocks - (m0 >> 1);          // gallery blocks from the band's first diagonal block on
   const int jf = (h - 1) / 2;                      // leading columns that hold fewer than h valid tiles: 2, 4, ...
   const int jt = avail < jf ? (avail < 0 ? 0 : avail) : jf;
@@ -250,19 +250,19 @@ __host__ __device__ __forceinline__ int sym_band_tiles(int b, int m_blocks, int 
   const int flat = avail - jf;
   return jt * (jt + 1) + (flat > 0 ? flat * h : 0);
 }
-__host__ __device__ __forceinline__ int sym_total_tiles(int m_blocks, int n_blocks) {
+__host__ __device__ __forceinline__ int sym_total_tiles(int m_blocks, int n_blocks, int band) {
   int t = 0;
-  for (int b = 0; b * BAND < m_blocks; ++b) t += sym_band_tiles(b, m_blocks, n_blocks, nullptr, nullptr);
+  for (int b = 0; b * band < m_blocks; ++b) t += sym_band_tiles(b, m_blocks, n_blocks, band, nullptr, nullptr);
   return t;
 }
-__device__ __forceinline__ TileCoord sym_decode_tile(int tile, int m_blocks, int n_blocks) {
+__device__ __forceinline__ TileCoord sym_decode_tile(int tile, int m_blocks, int n_blocks, int band) {
   int b = 0, h = 0, jt = 0;
   for (;; ++b) {
-    const int tb = sym_band_tiles(b, m_blocks, n_blocks, &h, &jt);
+    const int tb = sym_band_tiles(b, m_blocks, n_blocks, band, &h, &jt);
     if (tile < tb) break;
     tile -= tb;
   }
-  const int m0 = b * BAND, n0 = m0 >> 1;
+  const int m0 = b * band, n0 = m0 >> 1;
   TileCoord t;
   if (tile < jt * (jt + 1)) {
     int j = 0;
@@ -277,27 +277,27 @@ __device__ __forceinline__ TileCoord sym_decode_tile(int tile, int m_blocks, int
 
 // CTA-pair symmetric mode: square 256 x 256 pair tiles (mp, n) with n >= mp, bands of BAND/2 pair rows;
 // inside a band the first h columns form a triangle (column j holds rows 0..j), the rest are full.
-__host__ __device__ __forceinline__ int sym_pair_band_tiles(int b, int Mp, int* h_out) {
-  constexpr int PB = BAND / 2;
+__host__ __device__ __forceinline__ int sym_pair_band_tiles(int b, int Mp, int band, int* h_out) {
+  const int PB = band / 2;
   const int p0 = b * PB;
   const int h = (PB < Mp - p0) ? PB : (Mp - p0);
   if (h_out) *h_out = h;
   return h * (h + 1) / 2 + (Mp - p0 - h) * h;
 }
-__host__ __device__ __forceinline__ int sym_pair_total(int Mp) {
+__host__ __device__ __forceinline__ int sym_pair_total(int Mp, int band) {
   int t = 0;
-  for (int b = 0; b * (BAND / 2) < Mp; ++b) t += sym_pair_band_tiles(b, Mp, nullptr);
+  for (int b = 0; b * (band / 2) < Mp; ++b) t += sym_pair_band_tiles(b, Mp, band, nullptr);
   return t;
 }
 // -> m_blk = pair row (units of 256 rows), n_blk = column block
-__device__ __forceinline__ TileCoord sym_pair_decode(int pt, int Mp) {
+__device__ __forceinline__ TileCoord sym_pair_decode(int pt, int Mp, int band) {
   int b = 0, h = 0;
   for (;; ++b) {
-    const int tb = sym_pair_band_tiles(b, Mp, &h);
+    const int tb = sym_pair_band_tiles(b, Mp, band, &h);
     if (pt < tb) break;
     pt -= tb;
   }
-  const int p0 = b * (BAND / 2);
+  const int p0 = b * (band / 2);
   TileCoord t;
   const int tri = h * (h + 1) / 2;
   if (pt < tri) {
@@ -314,9 +314,9 @@ __device__ __forceinline__ TileCoord sym_pair_decode(int pt, int Mp) {
 // tile -> (128-row query block, 256-column gallery block) of THIS CTA
 template <bool CTA2>
 __device__ __forceinline__ TileCoord tile_coord(int tile, int cta_rank, int m_blocks, int n_blocks, int symmetric, int band) {
-  if (!CTA2) return symmetric ? sym_decode_tile(tile, m_blocks, n_blocks) : decode_tile(tile, m_blocks, n_blocks, band);
+  if (!CTA2) return symmetric ? sym_decode_tile(tile, m_blocks, n_blocks, band) : decode_tile(tile, m_blocks, n_blocks, band);
   if (!symmetric) return decode_tile(tile + cta_rank, m_blocks, n_blocks, band);
-  TileCoord t = sym_pair_decode(tile >> 1, m_blocks >> 1);
+  TileCoord t = sym_pair_decode(tile >> 1, m_blocks >> 1, band);
   t.m_blk = 2 * t.m_blk + cta_rank;
   return t;
 }
@@ -364,7 +364,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   // CTA pairs count tiles in units of one CTA (two per pair tile) so that the loops below are shared
-  const int total_tiles = symmetric ? (CTA2 ? 2 * sym_pair_total(m_blocks >> 1) : sym_total_tiles(m_blocks, n_blocks)) : m_blocks * n_blocks;
+  const int total_tiles = symmetric ? (CTA2 ? 2 * sym_pair_total(m_blocks >> 1, band) : sym_total_tiles(m_blocks, n_blocks, band)) : m_blocks * n_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.b_hi);
@@ -651,10 +651,6 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   if (CTA2) m_blocks += m_blocks & 1;   // pairs take two vertically adjacent 128-row blocks; a padding block is all out of range
   const int n_blocks = (int)ceil_div(G, BN);
   MPREID_REQUIRE((int64_t)m_blocks * n_blocks < INT32_MAX, "dist_tc: too many tiles");
-  const int64_t total = symmetric ? (CTA2 ? 2 * (int64_t)sym_pair_total(m_blocks >> 1) : sym_total_tiles(m_blocks, n_blocks)) : (int64_t)m_blocks * n_blocks;
-  const int sms = sm_count_of_current_device();
-  int grid = (int)(total < sms ? total : sms);
-  if (CTA2) grid &= ~1;
   constexpr int STAGE_BYTES = (C::PLANES * BM + PlanesB<PREC>::value * BN_LOCAL) * ROW_BYTES;
   constexpr int NSTAGES = CTA2 ? pair_stages(STAGE_BYTES) : C::STAGES * (128 / ROW_BYTES);
   const int smem = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
@@ -683,6 +679,10 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   band += band & 1;
   if (const char* band_env = getenv("MPREID_GEMM_BAND")) { const int b = atoi(band_env); if (b >= 2 && !(b & 1)) band = b; }
   const int Qi = (int)Q, Gi = (int)G;
+  const int64_t total = symmetric ? (CTA2 ? 2 * (int64_t)sym_pair_total(m_blocks >> 1, band) : sym_total_tiles(m_blocks, n_blocks, band)) : (int64_t)m_blocks * n_blocks;
+  const int sms = sm_count_of_current_device();
+  int grid = (int)(total < sms ? total : sms);
+  if (CTA2) grid &= ~1;
   if (CTA2) {
     MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     cudaLaunchConfig_t cfg;
