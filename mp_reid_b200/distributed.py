@@ -134,3 +134,166 @@ def rerank_sharded(prep_all: "E.Prepared", nq: int, k1: int, k2: int, lambda_val
     q_ids = ids32[:nq_local].contiguous()
     final_local = E.rerank_finish(nbr_all, v0_all, rows[:nq_local], q_ids, rm[:nq_local], N, nq, k1, k2, lambda_value)  # :73-99
     return final_local, (q_lo, q_hi)
+
+
+# ------------------------------------------------------------------------------------------------
+# Cooperative evaluation from host memory: every rank feeds ITS queries and ITS slice of the gallery
+# (what a sharded feature extraction leaves on each rank), the slices travel once over NVLink.
+def aligned_shard_bounds(n: int, world: int, rank: int, align: int = 32) -> tuple[int, int]:
+    """Contiguous row shard [lo, hi) whose start is a multiple of `align` (column blocks of the distance
+    matrix then start 128-byte aligned and keep the vector-store path); the last shards may be short or empty."""
+    per = ((n + world - 1) // world + align - 1) // align * align
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def _metrics():
+    from . import metrics   # late: metrics imports this module lazily too
+    return metrics
+
+
+def sharded_evaluator(num_query_local: int, **kw):
+    """R1_mAP_eval whose compute() is cooperative over the ranks of `group` (keyword, default WORLD): update() takes
+    this rank's query batches followed by this rank's gallery batches.  See R1_mAP_eval_sharded.compute."""
+    return _make_sharded_class()(num_query_local, **kw)
+
+
+_SHARDED_CLS = None
+
+
+def _make_sharded_class():
+    global _SHARDED_CLS
+    if _SHARDED_CLS is not None:
+        return _SHARDED_CLS
+    M = _metrics()
+
+    class R1_mAP_eval_sharded(M.R1_mAP_eval):
+        """Same surface as R1_mAP_eval (utils/metrics.py:91-134); every rank calls reset / update / compute.
+
+        Rank r holds `num_query` of the queries and a contiguous slice of the gallery (slices in rank order form the
+        gallery).  compute(): each slice is broadcast from its owner in sub-blocks (NCCL over NVLink, asynchronous,
+        on a side stream) straight into its place in a [G, D] buffer, so the distance GEMM of one sub-block overlaps the
+        upload and transfer of the next ones and the columns keep the global gallery order (ties break exactly as on
+        one GPU); every rank ranks its own queries; the per-query results are all-gathered once and reduced by numpy in
+        global query order: every rank returns the same (cmc, mAP) as a one-GPU evaluation of all queries.
+        distmat / qf are this rank's rows, gf the full normalised gallery.
+        """
+
+        def __init__(self, num_query, *args, group=None, **kw):
+            super().__init__(num_query, *args, **kw)
+            self._group = group
+
+        def reset(self):
+            super().reset()
+            self._lab_dev = []
+
+        def update(self, output):
+            super().update(output)
+            # labels ride the upload stream right behind their features: a host->device copy issued later, from
+            # compute(), would queue behind every feature piece on the copy engine and hold back the exchange
+            _, pid, camid = output
+            dev = M._device()
+            lab = np.stack([np.asarray(pid, dtype=np.int64).reshape(-1), np.asarray(camid, dtype=np.int64).reshape(-1)])
+            cs = M._copy_stream(dev)
+            with torch.cuda.stream(cs):
+                # pinned staging: a pageable source would make this call wait for the feature copies queued ahead of it
+                self._lab_dev.append(torch.from_numpy(lab).pin_memory().to(dev, non_blocking=True))
+
+        def compute(self):
+            if self.reranking:
+                raise NotImplementedError("sharded evaluator: use distributed.rerank_sharded for re-ranking")
+            if self.feat_norm:
+                print("The test feature is normalized")
+            print('=> Computing DistMat with euclidean_distance')
+            group, norm = self._group, bool(self.feat_norm)
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            nq = self.num_query
+            q_parts, g_parts = self._split_rows()
+            dev = M._device()
+            n_loc = sum(t.shape[0] for _, t in g_parts)
+            D = (q_parts[0][1] if q_parts else g_parts[0][1]).shape[1]
+            # sizes + labels of every slice: two small all-gathers (slice sizes may differ); no host->device copy here
+            meta = torch.empty((2,), dtype=torch.int64, device=dev)
+            meta[0].fill_(nq); meta[1].fill_(n_loc)
+            metas = torch.empty((world, 2), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(metas.view(-1), meta, group=group)
+            metas = metas.cpu().numpy()
+            q_counts, g_counts = [int(x) for x in metas[:, 0]], [int(x) for x in metas[:, 1]]
+            S = max(g_counts + [1])
+            num_g = int(sum(g_counts))
+            offs = np.concatenate([[0], np.cumsum(g_counts)]).astype(np.int64)
+            # Every slice travels in sub-blocks of <= MPREID_SHARD_SUB_ROWS rows (multiples of 32: aligned columns), one
+            # broadcast each, issued asynchronously in the order (sub-block, owner) on a side stream that waits only for
+            # the upload pieces that sub-block needs: the GEMMs of early sub-blocks run while later ones are still on
+            # PCIe / NVLink, and the compute stream never waits for more than it is about to use.
+            import os
+            sub = max(32, int(os.environ.get("MPREID_SHARD_SUB_ROWS", "8192")) // 32 * 32)
+            gfull = torch.empty((num_g, D), dtype=torch.float32, device=dev)
+            xs = M._side_stream(dev, "exchange")
+            main = torch.cuda.current_stream(dev)
+            xs.wait_stream(main)                       # gfull exists, labels gathered
+            copied, next_piece = 0, 0
+            n_sub = [(c + sub - 1) // sub for c in g_counts]
+            stages = max(n_sub + [0])
+
+            def exchange(j):
+                """Enqueue (side stream) the broadcasts of sub-block j of every slice -> [(lo, hi, work)]."""
+                nonlocal copied, next_piece
+                out = []
+                with torch.cuda.stream(xs):
+                    for r in range(world):
+                        if j >= n_sub[r]:
+                            continue
+                        lo = int(offs[r]) + j * sub
+                        hi = min(int(offs[r + 1]), lo + sub)
+                        if r == rank:
+                            need = hi - int(offs[r])   # own rows that must have landed
+                            while copied < need:
+                                bi, t = g_parts[next_piece]
+                                ev = self._events[bi]
+                                if ev is not None:
+                                    xs.wait_event(ev)
+                                else:
+                                    xs.wait_stream(main)
+                                gfull[int(offs[r]) + copied: int(offs[r]) + copied + t.shape[0]].copy_(t, non_blocking=True)
+                                copied += t.shape[0]; next_piece += 1
+                        src = dist.get_global_rank(group, r) if group is not None else r
+                        out.append((lo, hi, dist.broadcast(gfull[lo:hi], src=src, group=group, async_op=True)))
+                return out
+
+            # queries of this rank
+            self._wait(0, (q_parts[-1][0] + 1) if q_parts else 0)
+            qv = M._merge_adjacent([t for _, t in q_parts])
+            q = E.prep_rows(qv[0] if len(qv) == 1 else torch.cat(qv, dim=0), normalize=norm, precision=self._precision, keep_xn=True)
+            dmat = E.alloc_dist(nq, num_g, dev)
+            gf = torch.empty((num_g, D), dtype=torch.float32, device=dev)
+            # host-side software pipeline: the broadcasts of stage j+1 are enqueued before the GEMMs of stage j (an NCCL
+            # call costs ~0.1 ms of host time; issuing all of them up front would delay the first GEMM by milliseconds)
+            pending = exchange(0) if stages else []
+            for j in range(stages):
+                nxt = exchange(j + 1) if j + 1 < stages else []
+                for lo, hi, work in pending:
+                    work.wait()                        # the compute stream waits for this sub-block only
+                    g = E.prep_rows(gfull[lo:hi], normalize=norm, precision=self._precision, xn_out=gf[lo:hi])
+                    E.dist_matrix(q, g, self._metric, self._precision, out=dmat[:, lo:hi])
+                pending = nxt
+            # labels last: they were uploaded behind their features, the late ones land when the last piece does
+            main.wait_stream(M._copy_stream(dev))
+            lab_all = torch.cat(self._lab_dev, dim=1) if self._lab_dev else torch.zeros((2, 0), dtype=torch.int64, device=dev)
+            lab = torch.zeros((2, S), dtype=torch.int64, device=dev)
+            lab[:, :n_loc] = lab_all[:, nq:nq + n_loc]
+            labs = torch.empty((world * 2, S), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(labs, lab, group=group)
+            labs = labs.view(world, 2, S)
+            g_pid = torch.cat([labs[r, 0, :g_counts[r]] for r in range(world)])
+            g_cam = torch.cat([labs[r, 1, :g_counts[r]] for r in range(world)])
+            fh, ap, nr = E.rank_eval(dmat, lab_all[0, :nq].contiguous(), g_pid, lab_all[1, :nq].contiguous(), g_cam, self._junk)
+            max_rank = 50
+            if num_g < max_rank:
+                max_rank = num_g
+                print("Note: number of gallery samples is quite small, got {}".format(num_g))
+            cmc, mAP = sharded_reduce(fh, ap, nr, q_counts, max_rank, num_g, group)
+            return cmc, mAP, M.LazyDistmat(dmat), self.pids, self.camids, q.xn, gf
+
+    _SHARDED_CLS = R1_mAP_eval_sharded
+    return _SHARDED_CLS

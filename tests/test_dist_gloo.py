@@ -83,3 +83,11 @@ def test_dropin_seeds_only_the_two_hot_path_modules(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "META mp_reid_b200.metrics utils.meter mp_reid_b200.metrics mp_reid_b200.reranking" in out.stdout
+
+
+def test_aligned_shard_bounds_cover_and_align():
+    from mp_reid_b200.distributed import aligned_shard_bounds
+    for n, w in [(82161, 8), (82161, 2), (100, 8), (0, 4), (33, 2), (9003, 2), (15913, 4)]:
+        b = [aligned_shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all(lo % 32 == 0 or lo == n for lo, _ in b)

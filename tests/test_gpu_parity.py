@@ -338,6 +338,18 @@ def test_single_process_multi_gpu_evaluator(monkeypatch):
         assert torch.equal(qf0, qf1) and torch.equal(gf0, gf1) and len(p1) == Q + G
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_evaluator_under_torchrun():
+    """distributed.sharded_evaluator (every rank uploads its queries and its gallery slice, NCCL broadcasts): same
+    cmc / mAP / matrices as one GPU, bit for bit (the check itself lives in scripts/sharded_eval_check.py)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "sharded_eval_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_EVAL_OK 2" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_evaluator_reranking_flag(golden_dir, capsys):
     g = load(golden_dir, "rerank_small")
     ev = metrics.R1_mAP_eval(len(g["qf"]), reranking=True)
