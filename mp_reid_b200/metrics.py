@@ -246,6 +246,19 @@ def _fan_out(blk0, devs):
         return [blk0] + [blk0.to(d, non_blocking=True) for d in devs[1:]]
 
 
+def _take_rows(pend, rows_out):
+    """Split the pending row views into the first `rows_out` rows (adjacent views merged) and the remainder."""
+    take, got, rest = [], 0, []
+    for t in pend:
+        if got + t.shape[0] <= rows_out:
+            take.append(t); got += t.shape[0]
+        elif got < rows_out:
+            take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
+        else:
+            rest.append(t)
+    return _merge_adjacent(take), rest
+
+
 def _merge_adjacent(views):
     """Row views that follow each other in the same allocation (the pieces of one upload) -> one view."""
     out = []
@@ -382,15 +395,7 @@ class R1_mAP_eval():
 
             def flush(rows_out):
                 nonlocal pend, pend_rows, off
-                take, got, rest = [], 0, []
-                for t in pend:
-                    if got + t.shape[0] <= rows_out:
-                        take.append(t); got += t.shape[0]
-                    elif got < rows_out:
-                        take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
-                    else:
-                        rest.append(t)
-                take = _merge_adjacent(take)   # pieces of one upload are neighbouring views: no copy
+                take, rest = _take_rows(pend, rows_out)   # pieces of one upload are neighbouring views: no copy
                 blk = take[0] if len(take) == 1 else torch.cat(take, dim=0)
                 g = E.prep_rows(blk, normalize=norm, precision=self._precision, xn_out=gf[off:off + rows_out])
                 E.dist_matrix(q, g, self._metric, self._precision, out=dist[:, off:off + rows_out])
@@ -444,15 +449,7 @@ class R1_mAP_eval():
         def flush(rows_out):
             # the chunk is assembled on device 0, broadcast to the peers over NVLink, then contracted everywhere
             nonlocal pend, pend_rows, off
-            take, got, rest = [], 0, []
-            for t in pend:
-                if got + t.shape[0] <= rows_out:
-                    take.append(t); got += t.shape[0]
-                elif got < rows_out:
-                    take.append(t[: rows_out - got]); rest.append(t[rows_out - got:]); got = rows_out
-                else:
-                    rest.append(t)
-            take = _merge_adjacent(take)
+            take, rest = _take_rows(pend, rows_out)
             blk0 = take[0] if len(take) == 1 else torch.cat(take, dim=0)
             blks = _fan_out(blk0, devs)
             for k, dev in enumerate(devs):

@@ -143,3 +143,19 @@ def test_merge_adjacent_views_is_copy_free_and_exact():
     cols = t[:, :2]                                                                 # column slices are not contiguous rows
     assert len(_merge_adjacent([cols[0:2], cols[2:4]])) == 2
     assert _merge_adjacent([]) == []
+
+
+def test_take_rows_splits_pending_views_exactly():
+    import torch
+    from mp_reid_b200.metrics import _take_rows
+    t = torch.arange(80.).reshape(20, 4)
+    u = torch.ones(5, 4)
+    for cut in (0, 1, 7, 8, 12, 13, 20, 25):
+        pend = [t[0:8], t[8:12], u, t[12:20]]
+        take, rest = _take_rows(pend, cut)
+        whole = torch.cat(pend)
+        got = torch.cat(take) if take else whole[:0]
+        left = torch.cat(rest) if rest else whole[:0]
+        assert torch.equal(got, whole[:cut]) and torch.equal(left, whole[cut:]), cut
+    take, rest = _take_rows([t[0:8], t[8:12]], 12)
+    assert len(take) == 1 and take[0].data_ptr() == t.data_ptr() and rest == []
