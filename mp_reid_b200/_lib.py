@@ -63,11 +63,18 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise RuntimeError(f"{LIB_PATH} is missing; run `python -m mp_reid_b200.build`")
-        from . import build as _build
         _build.build()
+    elif not _build.is_current():
+        # the .so is git-ignored: after an edit of csrc/ a stale build would be loaded silently (the ABI version does not
+        # change with a kernel), so the source hash written at build time is checked on every load
+        if build_if_missing and _build.have_nvcc():
+            _build.build()
+        else:
+            raise RuntimeError(f"{LIB_PATH} was built from other sources than the ones in csrc/; run `python -m mp_reid_b200.build`")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

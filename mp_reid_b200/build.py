@@ -33,6 +33,16 @@ def _stamp():
     return h.hexdigest()
 
 
+def have_nvcc() -> bool:
+    return os.path.exists(_nvcc())
+
+
+def is_current() -> bool:
+    """True if the built library carries the stamp of the sources in csrc/ and include/."""
+    stamp_file = LIB + ".stamp"
+    return os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == _stamp()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     stamp_file = LIB + ".stamp"
     stamp = _stamp()

@@ -64,8 +64,9 @@ k_prep_rows(const float* __restrict__ x, int64_t rows, int D, int64_t ld_x, int 
         mx = block_max_128(mx, sh);
         if (normalize) mx = mx / den;
         // power-of-two row scale: max|xn| * 2^s in [512, 1024) keeps hi AND lo in fp16's normal range
+        // (the exponent is clamped so that both 2^s and 2^-s stay normal fp32 numbers: rows below 2^-116 keep 2^126)
         int e = 0;
-        if (mx > 0.f && mx < INFINITY) { (void)frexpf(mx, &e); hscale = ldexpf(1.0f, 10 - e); }
+        if (mx > 0.f && mx < INFINITY) { (void)frexpf(mx, &e); hscale = ldexpf(1.0f, min(10 - e, 126)); }
         if (threadIdx.x == 0) h_scale_inv[r] = 1.0f / hscale;
       }
     }

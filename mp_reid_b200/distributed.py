@@ -16,6 +16,46 @@ import torch.distributed as dist
 from . import engine as E
 
 
+# ------------------------------------------------------------------------------------------------
+# Collectives.  NCCL is the product path.  With any other backend (gloo: the CPU tests, and the two-ranks-on-ONE-GPU
+# GPU test, which NCCL refuses) device tensors are staged through host memory, so the same code runs everywhere.
+def _is_nccl(group=None) -> bool:
+    return dist.get_backend(group) == "nccl"
+
+
+class _StreamWork:
+    """Stand-in for the Work handle of an asynchronous NCCL call: wait() makes the current stream wait for `event`."""
+
+    def __init__(self, event=None):
+        self.event = event
+
+    def wait(self):
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+
+
+def all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None):
+    if inp.is_cuda and not _is_nccl(group):
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, inp.cpu(), group=group)
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+
+
+def broadcast(t: torch.Tensor, src: int, group=None, async_op: bool = False):
+    """dist.broadcast; returns an object with wait() when async_op (the current stream then waits for the data)."""
+    if t.is_cuda and not _is_nccl(group):
+        host = t.cpu()                                   # synchronises the current stream: the source rows are complete
+        dist.broadcast(host, src=src, group=group)
+        t.copy_(host)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return _StreamWork(ev)
+    work = dist.broadcast(t, src=src, group=group, async_op=async_op)
+    return work if async_op else _StreamWork()
+
+
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous, balanced row shard [lo, hi) of n rows for `rank` of `world`."""
     base, rem = divmod(n, world)
@@ -33,7 +73,7 @@ def broadcast_gallery(gf: torch.Tensor | None, g_pid, g_cam, shape=None, src: in
     gshape, g_pid, g_cam = meta[0]
     if rank != src:
         gf = torch.empty(gshape, dtype=torch.float32, device=device)
-    dist.broadcast(gf, src=src, group=group)
+    broadcast(gf, src, group)
     return gf, g_pid, g_cam
 
 
@@ -51,7 +91,7 @@ def gather_per_query(first_hit: torch.Tensor, ap: torch.Tensor, num_rel: torch.T
     packed[1, :n] = ap
     packed[2, :n] = num_rel.to(torch.float64)
     out = torch.empty((world * 3, width), dtype=torch.float64, device=ap.device)  # concatenation along dim 0
-    dist.all_gather_into_tensor(out, packed, group=group)
+    all_gather_into(out, packed, group)
     h = out.cpu().numpy().reshape(world, 3, width)
     fh = np.concatenate([h[r, 0, :counts[r]] for r in range(world)]).astype(np.int32)
     apv = np.concatenate([h[r, 1, :counts[r]] for r in range(world)])
@@ -94,7 +134,7 @@ def _allgather_rows(x_local: torch.Tensor, ids_all: list[torch.Tensor], N: int, 
     pad = torch.zeros((width,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
     pad[: x_local.shape[0]] = x_local
     out = torch.empty((world * width,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
+    all_gather_into(out, pad, group)
     full = torch.empty((N,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
     for r in range(world):
         n = int(ids_all[r].numel())
@@ -216,7 +256,7 @@ def _make_sharded_class():
             meta = torch.empty((2,), dtype=torch.int64, device=dev)
             meta[0].fill_(nq); meta[1].fill_(n_loc)
             metas = torch.empty((world, 2), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(metas.view(-1), meta, group=group)
+            all_gather_into(metas.view(-1), meta, group)
             metas = metas.cpu().numpy()
             q_counts, g_counts = [int(x) for x in metas[:, 0]], [int(x) for x in metas[:, 1]]
             S = max(g_counts + [1])
@@ -258,7 +298,7 @@ def _make_sharded_class():
                                 gfull[int(offs[r]) + copied: int(offs[r]) + copied + t.shape[0]].copy_(t, non_blocking=True)
                                 copied += t.shape[0]; next_piece += 1
                         src = dist.get_global_rank(group, r) if group is not None else r
-                        out.append((lo, hi, dist.broadcast(gfull[lo:hi], src=src, group=group, async_op=True)))
+                        out.append((lo, hi, broadcast(gfull[lo:hi], src, group, async_op=True)))
                 return out
 
             # queries of this rank
@@ -283,7 +323,7 @@ def _make_sharded_class():
             lab = torch.zeros((2, S), dtype=torch.int64, device=dev)
             lab[:, :n_loc] = lab_all[:, nq:nq + n_loc]
             labs = torch.empty((world * 2, S), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(labs, lab, group=group)
+            all_gather_into(labs, lab, group)
             labs = labs.view(world, 2, S)
             g_pid = torch.cat([labs[r, 0, :g_counts[r]] for r in range(world)])
             g_cam = torch.cat([labs[r, 1, :g_counts[r]] for r in range(world)])

@@ -210,7 +210,7 @@ class RankResult:
         """-> (first_hit, ap, num_rel, status) numpy views of one pinned host copy (synchronises)."""
         host = torch.empty(self.buf.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(self.buf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.buf.device).synchronize()   # the copy runs on the stream of the buffer's device
         h = host.numpy()
         Q = self.Q
         return (h[8 * Q: 12 * Q].view(np.int32), h[: 8 * Q].view(np.float64), h[12 * Q: 16 * Q].view(np.int32),
@@ -287,7 +287,8 @@ def reduce_cmc_map(first_hit, ap, num_rel, max_rank: int, num_g: int, denominato
     num_rel = np.asarray(num_rel)
     valid = num_rel > 0
     n_valid = float(valid.sum())
-    assert n_valid > 0, "Error: all query identities do not appear in gallery"
+    if denominators == "valid":   # utils/metrics.py:82; the inline CLIP-style loop has no such check (mAP = 0, CMC = 0)
+        assert n_valid > 0, "Error: all query identities do not appear in gallery"
     fh = first_hit[valid].astype(np.int64)
     counts = np.bincount(np.minimum(fh, max_rank + 1), minlength=max_rank + 2)[1:max_rank + 1].cumsum()
     if denominators == "valid":

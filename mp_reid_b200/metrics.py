@@ -36,7 +36,11 @@ def _devices():
     if not spec:
         return [d0]
     ids = list(range(torch.cuda.device_count())) if spec == "all" else [int(x) for x in spec.split(",") if x.strip() != ""]
-    devs = [d0] + [torch.device(f"cuda:{i}") for i in ids if i != d0.index]
+    # the upload device comes first; an index listed twice gives two shards on that device (how the one-GPU test box
+    # exercises this path)
+    if d0.index in ids:
+        ids.remove(d0.index)
+    devs = [d0] + [torch.device(f"cuda:{i}") for i in ids]
     return devs
 
 
@@ -208,6 +212,17 @@ def _eval_device(dist_dev, q_pids, g_pids, q_camids, g_camids, max_rank, junk, d
     return E.reduce_cmc_map(first_hit, ap, num_rel, max_rank, num_g, denominators)
 
 
+def _dense_row_ranks(d: torch.Tensor) -> torch.Tensor:
+    """fp32 matrix whose rows order exactly like the rows of `d` (any float dtype): equal values -> equal ranks."""
+    assert d.shape[1] < (1 << 24), "dense ranks are exact in float32 only below 2^24 columns"
+    vals, idx = torch.sort(d, dim=1, stable=True)
+    new = torch.ones(vals.shape, dtype=torch.bool, device=d.device)
+    new[:, 1:] = vals[:, 1:] != vals[:, :-1]
+    new[:, 1:] &= ~(torch.isnan(vals[:, 1:]) & torch.isnan(vals[:, :-1]))   # numpy: all NaNs tie (and sort last)
+    ranks = torch.cumsum(new, dim=1).to(torch.float32)
+    return torch.empty_like(ranks).scatter_(1, idx, ranks)
+
+
 def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50, *, junk=None):
     """utils/metrics.py:28-88 -> (all_cmc float32[max_rank], mAP float64).
 
@@ -218,9 +233,15 @@ def eval_func(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50, *, junk=
         d = distmat.device_tensor
     else:
         d = distmat if isinstance(distmat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(distmat))
-        if d.dtype != torch.float32:
-            d = d.float()  # the reference sorts whatever dtype it is given; the evaluator only ever passes fp32
         d = d.to(dev, non_blocking=True)
+        if d.dtype != torch.float32:
+            # The reference sorts whatever dtype it is given; the kernels rank fp32.  Narrower types widen exactly; a
+            # float64 matrix whose down-cast is not exact would get new ties, so it is replaced by its per-row dense
+            # ranks (exact in fp32 for G < 2^24), which order identically under the stable tie rule.
+            d32 = d.float()
+            if d.dtype == torch.float64 and not torch.equal(d32.double(), d):
+                d32 = _dense_row_ranks(d)
+            d = d32
         if d.stride(1) != 1:
             d = d.contiguous()
     return _eval_device(d, q_pids, g_pids, q_camids, g_camids, max_rank, junk)
@@ -239,6 +260,8 @@ def _fan_out(blk0, devs):
     ring / tree over NVLink instead of P-1 copies out of one GPU), plain peer-to-peer copies as the fallback."""
     if len(devs) == 1:
         return [blk0]
+    if len({d.index for d in devs}) < len(devs):   # several shards on one device (tests): nothing to move for those
+        return [blk0 if d == devs[0] else blk0.to(d, non_blocking=True) for d in devs]
     try:
         from torch.cuda import comm
         return list(comm.broadcast(blk0, devices=[d.index for d in devs]))
@@ -308,7 +331,8 @@ class R1_mAP_eval():
         feat = feat.detach()
         # the reference does feat.cpu() here (a synchronising D2H per batch, utils/metrics.py:106)
         if feat.is_cuda:
-            feats.append(feat.to(dev, dtype=torch.float32))
+            # a snapshot, like the reference's feat.cpu(): the caller may overwrite its output buffer before compute()
+            feats.append(feat.to(dev, dtype=torch.float32, copy=True))
             self._events.append(None)
         else:
             # upload on the side stream in pieces of <= MPREID_COPY_ROWS rows, one event each: compute() starts the
@@ -331,7 +355,7 @@ class R1_mAP_eval():
         self.camids.extend(camid)
 
     def _wait(self, lo, hi):
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(_device())   # the stream the kernels of compute() launch on (MPREID_DEVICE)
         for ev in self._events[lo:hi]:
             if ev is not None:
                 cur.wait_event(ev)
@@ -353,6 +377,10 @@ class R1_mAP_eval():
         return q_parts, g_parts
 
     def compute(self):  # called after each epoch
+        with torch.cuda.device(_device()):   # MPREID_DEVICE may name a GPU other than torch's current one
+            return self._compute()
+
+    def _compute(self):
         if self.feat_norm:
             print("The test feature is normalized")
         nq = self.num_query

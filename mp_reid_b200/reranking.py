@@ -40,7 +40,7 @@ def _rerank_device(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_va
 
 def re_ranking(probFea, galFea, k1, k2, lambda_value, local_distmat=None, only_local=False, *, precision=None):
     dev = _device()
-    query_num = probFea.size(0) if hasattr(probFea, "size") else len(probFea)
+    query_num = int(probFea.shape[0])   # tensors and numpy arrays alike
     if only_local:  # :33-34
         d = torch.as_tensor(np.asarray(local_distmat), dtype=torch.float32).to(dev)
         out = E.rerank_from_dist(d.t().contiguous(), query_num, k1, k2, lambda_value)

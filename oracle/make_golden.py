@@ -111,7 +111,23 @@ def digest(a: np.ndarray) -> str:
 
 
 # --------------------------------------------------------------------------------------
-def small_case(name, qf, gf, q_pid, g_pid, q_cam, g_cam, rerank_params=(), normalize=True):
+def local_matrix(n_all, seed=123, scale=0.5):
+    """A NON-symmetric fp32 [N, N] 'local distance' matrix (utils/reranking.py:43-44); tests regenerate it."""
+    return (np.random.RandomState(seed).rand(n_all, n_all) * scale).astype(np.float32)
+
+
+def only_local_matrix(n_all, seed=321):
+    """The matrix handed in with only_local=True (utils/reranking.py:33-34): squared distances of clustered integer
+    lattice points plus NON-symmetric integer noise, scaled by 2^-10 -- every value is exact in fp32, so the tests
+    regenerate it bit-for-bit on any machine; integer distances also tie on purpose."""
+    rs = np.random.RandomState(seed)
+    centers = rs.randint(0, 1000, size=(25, 4))
+    pts = centers[rs.randint(0, 25, size=n_all)] + rs.randint(-30, 31, size=(n_all, 4))
+    d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1) + rs.randint(0, 50, size=(n_all, n_all))
+    return (d.astype(np.float64) / 1024.0).astype(np.float32)
+
+
+def small_case(name, qf, gf, q_pid, g_pid, q_cam, g_cam, rerank_params=(), normalize=True, local_params=()):
     rm, rr = load_reference()
     jf = junk_eval_func(rm)
     if normalize:
@@ -149,6 +165,26 @@ def small_case(name, qf, gf, q_pid, g_pid, q_cam, g_cam, rerank_params=(), norma
         fd_u = rr.re_ranking(qn, gn, k1, k2, lam)  # as shipped (unstable sorts)
         cmc_u, mAP_u = quiet(rm.eval_func, fd_u, q_pid, g_pid, q_cam, g_cam)
         out[tag + "_ref_mAP"] = np.float64(mAP_u)
+    for (k1, k2, lam) in local_params:
+        # utils/reranking.py:33-34 (only_local) and :43-44 (local_distmat added to the squared distances).  The local
+        # matrix is regenerated by the tests from the same legacy RandomState (stable across numpy versions), not stored.
+        n_all = qn.shape[0] + gn.shape[0]
+        local = local_matrix(n_all)
+        tag = f"rrloc_{k1}_{k2}_{int(lam * 100)}"
+        with stable_sorts(rm, rr):
+            fd = rr.re_ranking(qn, gn, k1, k2, lam, local_distmat=local)
+            cmc, mAP = quiet(rm.eval_func, fd, q_pid, g_pid, q_cam, g_cam)
+        assert fd.dtype == np.float32
+        out[tag + "_final"] = fd
+        out[tag + "_cmc"], out[tag + "_mAP"] = cmc, np.float64(mAP)
+        tag = f"rronly_{k1}_{k2}_{int(lam * 100)}"
+        only = only_local_matrix(n_all)
+        with stable_sorts(rm, rr):
+            fd = rr.re_ranking(qn, gn, k1, k2, lam, local_distmat=only, only_local=True)
+            cmc, mAP = quiet(rm.eval_func, fd, q_pid, g_pid, q_cam, g_cam)
+        assert fd.dtype == np.float32
+        out[tag + "_final"] = fd
+        out[tag + "_cmc"], out[tag + "_mAP"] = cmc, np.float64(mAP)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(f"[golden] {name}: mAP ref={out['ref_mAP']:.12f} stable={out['ref_stable_mAP']:.12f}"
           + (f" junk={out['ref_junk_mAP']:.12f}" if "ref_junk_mAP" in out else ""))
@@ -178,7 +214,7 @@ def make_small():
     small_case("no_match", qf, gf, q_pid, g_pid, q_cam, g_cam)
     # 5. re-ranking, paper parameters and the evaluator's (50,15), noisy enough to be sensitive
     s = synth.make_set(100, 500, 32, 25, 4, seed=14, sigma=1.6)
-    small_case("rerank_small", *s, rerank_params=[(20, 6, 0.3), (50, 15, 0.3), (7, 2, 0.5)])
+    small_case("rerank_small", *s, rerank_params=[(20, 6, 0.3), (50, 15, 0.3), (7, 2, 0.5)], local_params=[(20, 6, 0.3)])
     # 6. cross-modality cam labels (datasets/mmmp.py:128), junk rule matters
     s = synth.make_set(64, 400, 48, 16, 6, seed=15, sigma=1.2, cross_modality=True)
     small_case("cctv_small", *s)
@@ -235,6 +271,8 @@ def make_full(which):
         print(f"[golden] {tag}: mAP={r['ref_mAP']:.15f} stable={r['ref_stable_mAP']:.15f} "
               f"dist {r['ref_dist_s']:.2f}s eval {r['ref_eval_s']:.2f}s")
 
+    if which == "c4s":
+        return make_sensitive_rerank(rm, rr)
     if which == "c1":
         evaluate("c1", "market", junk=True, cos=True)
     elif which == "c2":
@@ -247,6 +285,37 @@ def make_full(which):
         evaluate("c4", "msmt17")
     else:
         raise SystemExit("unknown --full target")
+
+
+# A SENSITIVE large re-ranking golden (sigma = 3 saturates the re-ranked mAP at ~0.99, which makes a
+# 1e-4 mAP gate nearly vacuous): an MSMT17-like subsample that the unmodified reference can still re-rank in this
+# container's 62 GB (N = 30,000 -> ~22 GB of N x N temporaries), noisy enough that the re-ranked mAP sits near 0.5.
+C4S = dict(Q=3700, G=26300, D=1280, n_id=980, n_cam=15, seed=21, sigma=3.9, k1=20, k2=6, lam=0.3)
+
+
+def make_sensitive_rerank(rm, rr):
+    c = C4S
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_set(c["Q"], c["G"], c["D"], c["n_id"], c["n_cam"], c["seed"], c["sigma"])
+    feats = torch.nn.functional.normalize(torch.cat([qf, gf]), dim=1, p=2)
+    qn, gn = feats[: c["Q"]], feats[c["Q"]:]
+    d = rm.euclidean_distance(qn, gn)
+    with stable_sorts(rm):
+        cmc0, mAP0 = quiet(rm.eval_func, d, q_pid, g_pid, q_cam, g_cam)
+    del d
+    t0 = time.time()
+    with stable_sorts(rm, rr):
+        fd = rr.re_ranking(qn, gn, c["k1"], c["k2"], c["lam"])
+    dt = time.time() - t0
+    with stable_sorts(rm):
+        cmc, mAP = quiet(rm.eval_func, fd, q_pid, g_pid, q_cam, g_cam)
+    rows = np.linspace(0, c["Q"] - 1, 8).astype(np.int64)
+    out = dict(params=np.array(json.dumps(c)), rows=rows, final_rows=fd[rows].astype(np.float32),
+               mAP=np.float64(mAP), cmc=cmc, pre_mAP=np.float64(mAP0), pre_cmc=cmc0,
+               final_sum=np.float64(fd.astype(np.float64).sum()), final_min=np.float32(fd.min()), final_max=np.float32(fd.max()),
+               row_sums=fd.astype(np.float64).sum(1), seconds=np.float64(dt), cores=np.int64(os.cpu_count()))
+    np.savez_compressed(os.path.join(OUT, "rerank_c4s.npz"), **out)
+    print(f"[golden] c4s: N={c['Q'] + c['G']} mAP {mAP0:.12f} -> re-ranked {mAP:.12f} (R1 {cmc0[0]:.4f} -> {cmc[0]:.4f}) "
+          f"in {dt:.1f}s on {os.cpu_count()} cores")
 
 
 if __name__ == "__main__":

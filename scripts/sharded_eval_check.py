@@ -1,15 +1,28 @@
-"""torchrun check of distributed.sharded_evaluator: ragged query / gallery shards fed per rank from host memory must
-give the cmc / mAP of a one-GPU evaluation of all queries, bit for bit.  Prints 'SHARDED_EVAL_OK' on rank 0."""
+"""torchrun check of the multi-rank paths: distributed.sharded_evaluator (ragged query / gallery shards fed per rank
+from host memory) and distributed.rerank_sharded (row-sharded k-reciprocal re-ranking) must give what ONE GPU gives,
+bit for bit.  Prints 'SHARDED_EVAL_OK <world>' on rank 0.
+
+    MPREID_CHECK_BACKEND=nccl|gloo   (default nccl; gloo stages device tensors through the host)
+    MPREID_CHECK_ONE_DEVICE=1        every rank uses cuda:0 (two ranks on a one-GPU box; needs gloo: NCCL refuses
+                                     two ranks on one device)
+"""
 import contextlib, io, os, sys
 import numpy as np, torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mp_reid_b200 import metrics, distributed as MD
+from mp_reid_b200 import engine as E, metrics, distributed as MD
+from mp_reid_b200.reranking import _rerank_device
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+backend = os.environ.get("MPREID_CHECK_BACKEND", "nccl")
+if os.environ.get("MPREID_CHECK_ONE_DEVICE", "0") == "1":
+    local = 0
 torch.cuda.set_device(local)
 os.environ["MPREID_DEVICE"] = f"cuda:{local}"
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if backend == "nccl":
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+else:
+    dist.init_process_group(backend)
 rng = np.random.RandomState(21)
 Q, G, D = 1501, 9003, 320
 x = torch.from_numpy(rng.randn(Q + G, D).astype(np.float32))
@@ -29,6 +42,19 @@ for junk in ("none", "pid_cam"):
         cmc0, mAP0, d0, *_, qf0, gf0 = ref.compute()
     assert np.array_equal(cmc, cmc0) and mAP == mAP0, (rank, junk, mAP, mAP0)
     assert np.array_equal(np.asarray(dmat), np.asarray(d0)[q_lo:q_hi]) and torch.equal(gf, gf0) and torch.equal(qf, qf0[q_lo:q_hi])
+
+# ---- row-sharded re-ranking: this rank's query rows of final_dist == the same rows of the one-GPU result
+dev = torch.device("cuda", local)
+centers = rng.randn(40, 96).astype(np.float32)
+lab = rng.randint(0, 40, 2300)
+feats = torch.from_numpy(centers[lab] + 1.3 * rng.randn(2300, 96).astype(np.float32)).to(dev)
+nq = 301
+prep = E.prep_rows(feats, normalize=True, keep_xn=False)
+for (k1, k2, lam) in [(20, 6, 0.3), (7, 1, 0.5)]:
+    want = _rerank_device(prep, nq, k1, k2, lam)
+    got, (lo, hi) = MD.rerank_sharded(prep, nq, k1, k2, lam)
+    assert (lo, hi) == MD.shard_bounds(nq, world, rank)
+    assert torch.equal(got, want[lo:hi]), (rank, k1, k2, float((got - want[lo:hi]).abs().max()))
 dist.barrier()
 if rank == 0:
     print("SHARDED_EVAL_OK", world)

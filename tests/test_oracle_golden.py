@@ -75,6 +75,20 @@ def test_re_ranking_bit_exact(golden_dir, name, params):
         assert abs(r["mAP"] - g[tag + "_ref_mAP"]) < 5e-3  # unstable-sort reference, tie-heavy fp16 output
 
 
+def test_re_ranking_local_distmat_and_only_local_bit_exact(golden_dir):
+    """utils/reranking.py:33-34 (only_local) and :43-44 (local_distmat added before the normalisation)."""
+    from oracle.make_golden import local_matrix, only_local_matrix
+    g = load(golden_dir, "rerank_small")
+    qn, gn = feats(g)
+    n_all = len(qn) + len(gn)
+    fd = orc.re_ranking(qn, gn, 20, 6, 0.3, local_distmat=local_matrix(n_all))
+    assert fd.dtype == np.float32 and np.array_equal(fd, g["rrloc_20_6_30_final"])
+    assert orc.rank_eval(fd, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])["mAP"] == g["rrloc_20_6_30_mAP"]
+    fd = orc.re_ranking(qn, gn, 20, 6, 0.3, local_distmat=only_local_matrix(n_all), only_local=True)
+    assert fd.dtype == np.float32 and np.array_equal(fd, g["rronly_20_6_30_final"])
+    assert orc.rank_eval(fd, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])["mAP"] == g["rronly_20_6_30_mAP"]
+
+
 def test_small_gallery_note_and_max_rank(golden_dir, capsys):
     g = load(golden_dir, "small_gallery")
     cmc, _ = orc.eval_func(g["dist_euclid"], g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
