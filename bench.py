@@ -372,7 +372,7 @@ def run_ours(args, data, workload):
         counts = [MD.shard_bounds(rq, world, r)[1] - MD.shard_bounds(rq, world, r)[0] for r in range(world)]
 
         def rr():
-            p = E.prep_rows(sub, normalize=True, precision=prec, keep_xn=False)
+            p = E.prep_rows(sub, normalize=True, precision=prec, keep_xn=True)   # the fused all-pairs pass reads feature rows
             if distributed:
                 dfin, _ = MD.rerank_sharded(p, rq, args.k1, args.k2, 0.3, prec)
             else:

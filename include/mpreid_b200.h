@@ -116,6 +116,26 @@ MPREID_API int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, cons
                                  int64_t N, int64_t K, int64_t ldk, int metric, int precision,
                                  float* out, int64_t ld_out, float* row_max, void* stream);
 
+/* Fused flavour of the all-pairs launch for re-ranking: utils/reranking.py:36-48 WITHOUT the (Q+G)^2 matrix in HBM.
+ * Squared-euclidean, symmetric tiles as above, but nothing is stored except
+ *   out_qg [Q, ld_out]  the query-to-gallery block the lambda blend needs (:95); element (q, g) sits at column
+ *                       (Q & 31) + g, so that 32-column groups keep their 128-byte alignment; ld_out >= (Q & 31) + N-Q;
+ *   row_max [N]         (pre-filled with -inf) the column maxima of :46;
+ *   cand [N, cand_cap], cand_cnt [N] (zeroed by the caller): every element d(i, j) <= thr[i] is appended to the
+ *                       candidate list of row i as (j << 32 | fp32 bits), in no particular order (both orientations of a
+ *                       mirrored tile append).  cand_cnt keeps counting past cand_cap.
+ * thr [N]: per-sample raw-domain thresholds, e.g. the (k+2)-th smallest distance to a sample of the columns plus a few
+ * ulps; mpreid_cand_topk then selects the first k of np.argsort(row / row_max, kind='stable') from the lists and
+ * reports in status[0] how many rows could NOT be decided from their list (overflow, fewer than k entries, or a
+ * possible tie with an element outside the list) -- the caller falls back to the materialising calls if it is not 0.
+ * status (device, int32[4]): [0] undecided rows, [1] longest list.                                              */
+MPREID_API int mpreid_dist_symmetric_topk(const void* xa, const void* xb, const float* x_sqnorm, const float* x_scale,
+                               int64_t N, int64_t K, int64_t ldk, int precision,
+                               const float* thr, uint64_t* cand, int32_t* cand_cnt, int64_t cand_cap,
+                               int64_t Q, float* out_qg, int64_t ld_out, float* row_max, void* stream);
+MPREID_API int mpreid_cand_topk(const uint64_t* cand, const int32_t* cand_cnt, int64_t cand_cap, int64_t N, int k,
+                     const float* row_scale, const float* thr, int32_t* idx, float* val, int32_t* status, void* stream);
+
 /* ---- ranking + CMC / AP ------------------------------------------------------------------------
  * Replaces eval_func (utils/metrics.py:28-88).  The Q x G argsort is never formed: for every query
  * the kernel takes the gallery entries with the query's pid (a hash-grouped label index), sorts
@@ -173,11 +193,25 @@ MPREID_API int mpreid_rerank_v0_capacity(int k1, int64_t N);
 MPREID_API int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, const int32_t* row_ids, int64_t R, int64_t N,
                            int k1, const int32_t* nbr_all, int K, const float* row_max_rows,
                            int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream);
+/* mpreid_rerank_build_v0 without matrix rows (fused all-pairs pass): original_dist[i, idx] (:70) is the stored neighbour
+ * value nbr_val_all[i, m] (already divided by the row maximum; the same accumulator the matrix would hold) when idx is
+ * the m-th neighbour of i, and (|x_i|^2 + |x_idx|^2 - 2 x_i.x_idx) / row_max in fp32 from the feature rows xn [N, ld_xn]
+ * for the few expansion members outside the neighbour list.                                                      */
+MPREID_API int mpreid_rerank_build_v0_sparse(const int32_t* row_ids, int64_t R, int64_t N, int k1, const int32_t* nbr_all,
+                                  const float* nbr_val_all, int K, const float* row_max_rows,
+                                  const float* xn, int64_t ld_xn, int64_t D, const float* sqnorm,
+                                  int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream);
 MPREID_API size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int k1, int k2);
 MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                          const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
                          int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                          float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
+/* mpreid_rerank_finish with the query rows given as the [Qs, G] block of query-to-gallery distances alone (column 0 =
+ * gallery sample 0, ld_dist >= N-Q): all that the fused all-pairs pass keeps of the (Q+G)^2 matrix (:72,95,99).      */
+MPREID_API int mpreid_rerank_finish_block(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                               const float* dist_qg, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
+                               int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                               float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);

@@ -31,7 +31,7 @@ int launch_dist_simt(const float* q, const float* g, const float* q_aux, const f
                      int64_t K, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max, cudaStream_t st);
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                    const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
-                   float* row_max, int symmetric, cudaStream_t st);
+                   float* row_max, int symmetric, cudaStream_t st, const TopkFuse* fuse);
 
 }  // namespace mpreid
 
@@ -69,7 +69,7 @@ extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
   MPREID_REQUIRE(precision == MPREID_BF16 || (qb && (gb || precision == MPREID_2XFP16)), "dist_matrix: the split modes need the lo planes");
   MPREID_REQUIRE((precision != MPREID_3XFP16 && precision != MPREID_2XFP16) || (q_scale && g_scale),
                  "dist_matrix: the FP16 split modes need the per-row scales");
-  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, 0, st);
+  return launch_dist_tc(qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, precision, out, ld_out, row_max, 0, st, nullptr);
 }
 
 extern "C" int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, const float* x_aux, const float* x_scale,
@@ -88,7 +88,7 @@ extern "C" int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, cons
   MPREID_REQUIRE(precision == MPREID_BF16 || xb, "dist_matrix_symmetric: the split modes need the lo plane");
   MPREID_REQUIRE((precision != MPREID_3XFP16 && precision != MPREID_2XFP16) || x_scale,
                  "dist_matrix_symmetric: the FP16 split modes need the per-row scales");
-  return launch_dist_tc(xa, xb, xa, xb, x_aux, x_aux, x_scale, x_scale, N, N, ldk, metric, precision, out, ld_out, row_max, 1, st);
+  return launch_dist_tc(xa, xb, xa, xb, x_aux, x_aux, x_scale, x_scale, N, N, ldk, metric, precision, out, ld_out, row_max, 1, st, nullptr);
 }
 
 extern "C" double mpreid_host_average_precision(const int32_t* ranks_host, int m, int64_t n) {
@@ -98,4 +98,23 @@ extern "C" double mpreid_host_average_precision(const int32_t* ranks_host, int m
 
 extern "C" void mpreid_host_order_keys(const float* values_host, int64_t n, uint32_t* keys_host) {
   for (int64_t i = 0; i < n; ++i) keys_host[i] = order_key(values_host[i]);
+}
+
+// Fused flavour of the all-pairs launch for re-ranking (utils/reranking.py:36-48 without the N x N matrix): see the header.
+extern "C" int mpreid_dist_symmetric_topk(const void* xa, const void* xb, const float* x_sqnorm, const float* x_scale,
+                                          int64_t N, int64_t K, int64_t ldk, int precision,
+                                          const float* thr, uint64_t* cand, int32_t* cand_cnt, int64_t cand_cap,
+                                          int64_t Q, float* out_qg, int64_t ld_out, float* row_max, void* stream) {
+  MPREID_REQUIRE(xa && x_sqnorm && thr && cand && cand_cnt && out_qg && row_max, "dist_symmetric_topk: null pointer");
+  MPREID_REQUIRE(N > 1 && K > 0 && ldk >= K && N < INT32_MAX && Q > 0 && Q < N, "dist_symmetric_topk: bad shape N=%lld Q=%lld", (long long)N, (long long)Q);
+  MPREID_REQUIRE(cand_cap >= 1 && cand_cap < (1 << 24) && ld_out >= (N - Q) + (Q & 31), "dist_symmetric_topk: bad candidate capacity / ld_out");
+  MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16 || precision == MPREID_2XFP16,
+                 "dist_symmetric_topk: needs a tensor-core precision mode");
+  MPREID_REQUIRE(precision == MPREID_BF16 || xb, "dist_symmetric_topk: the split modes need the lo plane");
+  MPREID_REQUIRE((precision != MPREID_3XFP16 && precision != MPREID_2XFP16) || x_scale, "dist_symmetric_topk: the FP16 split modes need the per-row scales");
+  TopkFuse f;
+  f.thr = thr; f.cand = (unsigned long long*)cand; f.cand_cnt = cand_cnt; f.cap = (int)cand_cap;
+  f.keep_rows = (int)Q; f.keep_col0 = (int)(Q & ~(int64_t)31);
+  return launch_dist_tc(xa, xb, xa, xb, x_sqnorm, x_sqnorm, x_scale, x_scale, N, N, ldk, MPREID_SQEUCLID, precision, out_qg, ld_out, row_max, 1,
+                        (cudaStream_t)stream, &f);
 }

@@ -142,6 +142,19 @@ HD double pairwise_sparse_sum(const int32_t* rank, int m, int64_t n) {
   return val[0];
 }
 
+// Fused top-k mode of the symmetric all-pairs launch (re-ranking, utils/reranking.py:46-48 without the N x N matrix):
+// instead of storing a tile and its transpose, the epilogue appends every element that is not above the per-sample
+// threshold to the candidate list of its row -- and, for mirrored tiles, of its column -- and stores only the
+// [Q, G] query-to-gallery block that the lambda blend needs (:95).
+struct TopkFuse {
+  const float* thr;              // [N] raw-domain threshold of sample i (as a row and, by symmetry, as a column)
+  unsigned long long* cand;      // [N, cap] entries (column << 32 | fp32 bits), unordered
+  int* cand_cnt;                 // [N] entries appended (keeps counting past cap: overflow is detected downstream)
+  int cap;
+  int keep_rows;                 // Q: rows < Q ...
+  int keep_col0;                 // ... and columns >= keep_col0 (= Q rounded down to 32) are stored at out[row, col - keep_col0]
+};
+
 // np.around(k1 / 2) -- round half to even (utils/reranking.py:60)
 HD int round_half_even_div2(int k1) {
   int h = k1 / 2;

@@ -325,15 +325,17 @@ struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
+static constexpr int kFuseQueue = 160;   // per-warp staging queue (entries); flushed with one atomic round per 32 entries
+
 // CTA-pair pipeline depth: as many stages as fit 192 KB (3 x 64 KB for the split-fp16 / TF32 modes)
 __host__ __device__ constexpr int pair_stages(int stage_bytes) { return (196608 / stage_bytes) < 8 ? (196608 / stage_bytes) : 8; }
 
-template <int PREC, int ROW_BYTES, int METRIC, bool VEC, bool CTA2>
+template <int PREC, int ROW_BYTES, int METRIC, bool VEC, bool CTA2, bool FUSE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, const float* __restrict__ g_aux,
           const float* __restrict__ q_scale, const float* __restrict__ g_scale, int Q, int G, int num_k_blocks,
           float* __restrict__ out, int64_t ld_out,
-          float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric, int band) {
+          float* __restrict__ row_max, int m_blocks, int n_blocks, int symmetric, int band, const TopkFuse fuse) {
   using C = Pipe<PREC, ROW_BYTES>;
   constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;            // gallery rows THIS CTA stages per k-block
   constexpr int A_PLANE = BM * ROW_BYTES, B_PLANE = BN_LOCAL * ROW_BYTES;
@@ -354,6 +356,8 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
   const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGES + 4);
   const uint32_t gvec_base = bar_base + 256u;              // 2 x 256 float2: per-column (aux, scale) of the tile
   const uint32_t stage_base = gvec_base + 2u * BN * 8u;    // 4 warps x 4 KB output staging
+  const uint32_t gthr_base = stage_base + 4u * 4096u;      // FUSE: 2 x 256 column thresholds, then 4 per-warp candidate queues
+  const uint32_t fq_base = gthr_base + 2u * BN * 4u;       //       (kFuseQueue x 8 B entries + kFuseQueue x 4 B rows each)
   // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tmem-empty barriers); the pair takes the
   // tiles (2p, 2p+1) of the band-major order, which are vertically adjacent (band heights are even)
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
@@ -479,6 +483,55 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     const int et = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw))) + (warp - 2) * 1024;
     float2* gvec_all = reinterpret_cast<float2*>(smem_raw + (gvec_base - smem_u32(smem_raw)));
+    // FUSE: column thresholds of the tile and this warp's candidate queue
+    float* gthr_all = reinterpret_cast<float*>(smem_raw + (gthr_base - smem_u32(smem_raw)));
+    unsigned long long* fq_ent = reinterpret_cast<unsigned long long*>(smem_raw + (fq_base - smem_u32(smem_raw))) + (warp - 2) * kFuseQueue;
+    int* fq_row = reinterpret_cast<int*>(smem_raw + (fq_base - smem_u32(smem_raw)) + 4 * kFuseQueue * 8) + (warp - 2) * kFuseQueue;
+    int fq_count = 0;                                  // warp-uniform
+    auto fq_flush = [&]() {
+      for (int e = lane; e < fq_count; e += 32) {
+        const int r = fq_row[e];
+        const int slot = atomicAdd(fuse.cand_cnt + r, 1);
+        if (slot < fuse.cap) fuse.cand[(int64_t)r * fuse.cap + slot] = fq_ent[e];
+      }
+      __syncwarp();
+      fq_count = 0;
+    };
+    // append this lane's hits: bit j of mrow = (row_a, col0 + j) qualifies for row row_a; bit j of mcol = it qualifies for
+    // the mirrored row col0 + j (column row_a).  Values are the lane's d[0..32).
+    auto fq_push = [&](uint32_t mrow, uint32_t mcol, int row_a, int col0, const float (&dv)[32]) {
+      const int n = __popc(mrow) + __popc(mcol);
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) return;
+      if (total > kFuseQueue) {
+        // thresholds that pass (almost) everything: no staging, every lane appends on its own (correct, slow; the
+        // candidate lists overflow in this regime anyway and the caller falls back to the materialising path)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {   // (fully unrolled: a dynamic index would move the value array to local memory)
+          if (mrow & (1u << j)) {
+            const int slot = atomicAdd(fuse.cand_cnt + row_a, 1);
+            if (slot < fuse.cap) fuse.cand[(int64_t)row_a * fuse.cap + slot] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(dv[j]);
+          }
+          if (mcol & (1u << j)) {
+            const int slot = atomicAdd(fuse.cand_cnt + col0 + j, 1);
+            if (slot < fuse.cap) fuse.cand[(int64_t)(col0 + j) * fuse.cap + slot] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(dv[j]);
+          }
+        }
+        return;
+      }
+      if (fq_count + total > kFuseQueue) fq_flush();
+      int pos = fq_count + incl - n;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (mrow & (1u << j)) { fq_ent[pos] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(dv[j]); fq_row[pos] = row_a; ++pos; }
+        if (mcol & (1u << j)) { fq_ent[pos] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(dv[j]); fq_row[pos] = col0 + j; ++pos; }
+      }
+      fq_count += total;
+      __syncwarp();
+    };
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric, band);
@@ -493,17 +546,22 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       const bool row_ok = gm < Q;
       const float qa = (row_ok && q_aux) ? q_aux[gm] : 0.f;
       const float qs = (kScaled && row_ok) ? q_scale[gm] : 1.f;
+      const float thr_r = (FUSE && row_ok) ? __ldg(fuse.thr + gm) : -INFINITY;
       float rmax = -INFINITY;
       float2* gvec = gvec_all + as * BN;
+      float* gthr = gthr_all + as * BN;
 #pragma unroll
       for (int c = et; c < BN; c += 128) {
         const int gn = t.n_blk * BN + c;
         float2 v = make_float2(1.f, 1.f);
+        float th = -INFINITY;
         if (gn < G) {
           if (g_aux) v.x = __ldg(g_aux + gn);
           if (kScaled) v.y = __ldg(g_scale + gn);
+          if (FUSE) th = __ldg(fuse.thr + gn);
         }
         gvec[c] = v;
+        if (FUSE) gthr[c] = th;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");   // gvec visible to the 4 epilogue warps
       mbar_wait(tfull_bar(as), aph);
@@ -531,36 +589,57 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
               d[j] = finish_distance<METRIC>(dot, qa, gv.x);
               if (gn0 + j < G) rmax = fmaxf(rmax, d[j]);
             }
-            // stage: lane == row, 16-byte chunk c of the row goes to position c ^ (row & 7)
+            // FUSE: only the [Q, G] block is stored (warp-uniform test), shifted so that 32-column groups stay aligned
+            const bool store_direct = !FUSE || (gm0 < fuse.keep_rows && gn0 >= fuse.keep_col0);
+            if (store_direct) {
+              // stage: lane == row, 16-byte chunk c of the row goes to position c ^ (row & 7)
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
-                  make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
-            __syncwarp();
-            // drain: 8 lanes cover one 128-byte row, 4 rows per instruction
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                    make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
+              __syncwarp();
+              const int row_lim = FUSE ? min(Q, fuse.keep_rows) : Q;
+              const int col_shift = FUSE ? fuse.keep_col0 : 0;
+              // drain: 8 lanes cover one 128-byte row, 4 rows per instruction
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = 4 * i + (lane >> 3), c = lane & 7;
-              const float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((c ^ (r & 7)) << 2));
-              const int grow = gm0 + r, gcol = gn0 + 4 * c;
-              if (grow < Q) {
-                float* dst = out + (int64_t)grow * ld_out + gcol;
-                if (VEC && gcol + 4 <= G) {
-                  __stcs(reinterpret_cast<float4*>(dst), v);   // streaming: the matrix must not evict the operand band from L2
-                } else {
-                  if (gcol < G) dst[0] = v.x;
-                  if (gcol + 1 < G) dst[1] = v.y;
-                  if (gcol + 2 < G) dst[2] = v.z;
-                  if (gcol + 3 < G) dst[3] = v.w;
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3), c = lane & 7;
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((c ^ (r & 7)) << 2));
+                const int grow = gm0 + r, gcol = gn0 + 4 * c;
+                if (grow < row_lim) {
+                  float* dst = out + (int64_t)grow * ld_out + (gcol - col_shift);
+                  if (VEC && gcol + 4 <= G) {
+                    __stcs(reinterpret_cast<float4*>(dst), v);   // streaming: the matrix must not evict the operand band from L2
+                  } else {
+                    if (gcol < G) dst[0] = v.x;
+                    if (gcol + 1 < G) dst[1] = v.y;
+                    if (gcol + 2 < G) dst[2] = v.z;
+                    if (gcol + 3 < G) dst[3] = v.w;
+                  }
                 }
               }
+              __syncwarp();
             }
-            __syncwarp();
+            if (FUSE) {
+              // candidates: one compare per element and side, hits (about 1 %) go through the warp queue
+              const uint32_t colmask = gn0 + 32 <= G ? 0xffffffffu : ((1u << (G - gn0)) - 1u);
+              uint32_t mrow = 0, mcol = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                mrow |= (d[j] <= thr_r ? 1u : 0u) << j;
+                mcol |= (d[j] <= gthr[cc + j] ? 1u : 0u) << j;
+              }
+              mrow &= colmask;
+              mcol = (mirror && row_ok) ? (mcol & colmask) : 0u;
+              fq_push(mrow, mcol, gm, gn0, d);
+            }
             if (mirror) {
               // transpose: for a fixed column the 32 lanes hold 32 consecutive rows -> one 128-byte store
+              if (!FUSE) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (row_ok && gn0 + j < G) __stcs(out + (int64_t)(gn0 + j) * ld_out + gm, d[j]);
+                for (int j = 0; j < 32; ++j)
+                  if (row_ok && gn0 + j < G) __stcs(out + (int64_t)(gn0 + j) * ld_out + gm, d[j]);
+              }
               if (row_max) {
                 // column maxima (the row maxima of the mirrored block): butterfly transpose-reduce, 31 shuffles
 #pragma unroll
@@ -589,6 +668,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       }
       if (row_max && row_ok && rmax > -INFINITY) atomic_max_f32(&row_max[gm], rmax);
     }
+    if (FUSE && fq_count) fq_flush();
   }
   tc_fence_before();
   if (CTA2) {
@@ -634,7 +714,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t ldk, 
 template <int PREC, int ROW_BYTES, bool CTA2>
 static int launch(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                   const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, float* out, int64_t ld_out, float* row_max,
-                  int symmetric, cudaStream_t st) {
+                  int symmetric, cudaStream_t st, const TopkFuse* fuse_in) {
   using C = Cfg<PREC>;
   constexpr int kpb = ROW_BYTES / C::ELEM;
   constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;
@@ -653,11 +733,17 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
   MPREID_REQUIRE((int64_t)m_blocks * n_blocks < INT32_MAX, "dist_tc: too many tiles");
   constexpr int STAGE_BYTES = (C::PLANES * BM + PlanesB<PREC>::value * BN_LOCAL) * ROW_BYTES;
   constexpr int NSTAGES = CTA2 ? pair_stages(STAGE_BYTES) : C::STAGES * (128 / ROW_BYTES);
-  const int smem = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/;
+  const bool fused = fuse_in != nullptr;
+  MPREID_REQUIRE(!fused || (symmetric && metric == MPREID_SQEUCLID), "dist_tc: the fused top-k mode is the symmetric squared-euclidean launch");
+  TopkFuse fuse;
+  memset(&fuse, 0, sizeof(fuse));
+  if (fused) fuse = *fuse_in;
+  const int smem = NSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 8 /*gvec*/ + 4 * 4096 /*staging*/ +
+                   (fused ? 2 * BN * 4 /*column thresholds*/ + 4 * kFuseQueue * 12 /*candidate queues*/ : 0);
   const bool vec = (ld_out % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true, CTA2>);   // no casts: a signature mismatch must not compile
+  using KernT = decltype(&k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true, CTA2, false>);   // no casts: a signature mismatch must not compile
   KernT kern = nullptr;
-#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, M, true, CTA2> : &k_dist_tc<PREC, ROW_BYTES, M, false, CTA2>
+#define MPREID_PICK(M) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, M, true, CTA2, false> : &k_dist_tc<PREC, ROW_BYTES, M, false, CTA2, false>
   switch (metric) {
     case MPREID_SQEUCLID: MPREID_PICK(MPREID_SQEUCLID); break;
     case MPREID_ARCCOS: MPREID_PICK(MPREID_ARCCOS); break;
@@ -665,6 +751,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
     default: MPREID_PICK(MPREID_SQRT_EUCLID); break;
   }
 #undef MPREID_PICK
+  if (fused) kern = vec ? &k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, true, CTA2, true> : &k_dist_tc<PREC, ROW_BYTES, MPREID_SQEUCLID, false, CTA2, true>;
   MPREID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nkb = (int)(ldk / kpb);
   // Query-band height of the tile order (m fastest inside a band): the band's operand planes must stay L2-resident
@@ -693,9 +780,9 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     MPREID_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max,
-                                         m_blocks, n_blocks, symmetric, band));
+                                         m_blocks, n_blocks, symmetric, band, fuse));
   } else {
-    kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max, m_blocks, n_blocks, symmetric, band);
+    kern<<<grid, THREADS, smem, st>>>(maps, q_aux, g_aux, q_scale, g_scale, Qi, Gi, nkb, out, ld_out, row_max, m_blocks, n_blocks, symmetric, band, fuse);
   }
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
@@ -705,7 +792,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
 
 int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* gb, const float* q_aux, const float* g_aux,
                    const float* q_scale, const float* g_scale, int64_t Q, int64_t G, int64_t ldk, int metric, int precision, float* out, int64_t ld_out,
-                   float* row_max, int symmetric, cudaStream_t st) {
+                   float* row_max, int symmetric, cudaStream_t st, const TopkFuse* fuse) {
   int dev = 0, major = 0;
   MPREID_CUDA_CHECK(cudaGetDevice(&dev));
   MPREID_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -715,7 +802,7 @@ int launch_dist_tc(const void* qa, const void* qb, const void* ga, const void* g
   }
   // pipeline shape: 128-byte smem rows (128B swizzle).  A 64-byte-row / twice-as-deep variant (template parameter
   // ROW_BYTES = 64) was measured 7 % slower at MSMT17 shape (6.18 vs 5.78 ms) and is not instantiated.
-#define MPREID_ARGS qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st
+#define MPREID_ARGS qa, qb, ga, gb, q_aux, g_aux, q_scale, g_scale, Q, G, ldk, metric, out, ld_out, row_max, symmetric, st, fuse
   // CTA pairs (cta_group::2, 256x256 tile per pair, 3 x 64 KB stages per CTA) for the rectangular GEMM of the
   // split-fp16 modes (rectangular and symmetric all-pairs); MPREID_GEMM_PAIR=0 selects the single-CTA kernel.
   const char* pair_env = getenv("MPREID_GEMM_PAIR");   // read per call: tests flip it inside one process

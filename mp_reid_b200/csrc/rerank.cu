@@ -146,8 +146,19 @@ __device__ __forceinline__ V0Smem v0_carve(unsigned char* base, const V0Sizes& z
   return s;
 }
 
+// Where the distances original_dist[i, idx] (:70) come from: the rows of the all-pairs matrix (dist != nullptr), or --
+// when the matrix was never written (fused all-pairs pass) -- the neighbour values of row i (the same accumulators, already
+// divided by the row maximum) for idx inside the top-K list, and an fp32 dot product of the feature rows for the few
+// expansion members outside it (typically < 20 per row: the 2/3 rule only admits sets that mostly overlap R(i)).
+struct V0Source {
+  const float* dist; int64_t ld;                    // matrix rows [R, >= N]
+  const float* nbr_val;                              // [N, K] divided neighbour values
+  const float* xn; int64_t ld_xn; int D;             // feature rows [N, D] fp32
+  const float* sqnorm;                               // [N]
+};
+
 __global__ void __launch_bounds__(kV0Threads)
-k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ row_ids, int R, int k1, int K, int Keff_in,
+k_build_v0(const V0Source src, const int32_t* __restrict__ row_ids, int R, int k1, int K, int Keff_in,
            const int32_t* __restrict__ nbr, const float* __restrict__ rowmax,
            int32_t* __restrict__ v0_col, uint16_t* __restrict__ v0_val, int32_t* __restrict__ v0_len, int C0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -220,11 +231,40 @@ k_build_v0(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict
     __syncthreads();
     const int nU = n_out;
     const float rmax = rowmax[il];
-    const float* drow = dist + (int64_t)il * ld;
-    for (int t = tid; t < nU; t += kV0Threads) {
-      const float dn = drow[s.list[t]] / rmax;          // original_dist[i, idx]  (:46)
-      s.w[t] = (float)exp((double)(-dn));               // np.exp on float32      (:70)
+    if (src.dist) {
+      const float* drow = src.dist + (int64_t)il * src.ld;
+      for (int t = tid; t < nU; t += kV0Threads) s.w[t] = drow[s.list[t]] / rmax;   // original_dist[i, idx]  (:46)
+    } else {
+      for (int t = tid; t < nU; t += kV0Threads) {
+        const int32_t x = s.list[t];
+        float dn = __int_as_float(0x7fc00000);          // NaN = "not a neighbour of i": computed below
+        for (int m = 0; m < K1; ++m) if (s.fwd[m] == x) { dn = src.nbr_val[(int64_t)i * K + m]; break; }
+        s.w[t] = dn;
+      }
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      const float* xi = src.xn + (int64_t)i * src.ld_xn;
+      const bool vec = (src.D & 3) == 0 && (src.ld_xn & 3) == 0 && ((uintptr_t)src.xn & 15) == 0;
+      for (int t = warp; t < nU; t += kV0Threads / 32) {
+        if (s.w[t] == s.w[t]) continue;                 // warp-uniform
+        const int32_t x = s.list[t];
+        const float* xx = src.xn + (int64_t)x * src.ld_xn;
+        float acc = 0.f;
+        if (vec) {
+          for (int c = lane * 4; c < src.D; c += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(xi + c)), b = __ldg(reinterpret_cast<const float4*>(xx + c));
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+          }
+        } else {
+          for (int c = lane; c < src.D; c += 32) acc = fmaf(__ldg(xi + c), __ldg(xx + c), acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __syncwarp();
+        if (lane == 0) s.w[t] = fmaf(-2.0f, acc, src.sqnorm[i] + src.sqnorm[x]) / rmax;   // utils/reranking.py:38-40,46
+      }
     }
+    __syncthreads();
+    for (int t = tid; t < nU; t += kV0Threads) s.w[t] = (float)exp((double)(-s.w[t]));   // np.exp on float32 (:70)
     __syncthreads();
     if (tid == 0) wsum_s = pairwise_sum_f32(s.w, nU);   // np.sum(weight)         (:71)
     __syncthreads();
@@ -386,67 +426,111 @@ __global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, cons
 }
 
 // ----------------------------------------------------------------------------------- Jaccard + blend
-static constexpr int kJacThreads = 512;
-static constexpr int kJacWarps = kJacThreads / 32;
+// Two kernels.  (1) k_blend_default: the dense part of :93-95 for gallery entries the query shares no V column with
+// (temp_min = 0 -> jaccard = 1 -> fp16(1 * fp16(1 - lambda))): a pure stream, 8 bytes per (query, gallery) pair, run
+// at full occupancy.  (2) k_jaccard_sparse: the fp16 min-accumulation (:86-92) over the inverted lists and the
+// overwrite of the few entries it touches.  Probe (oracle, k1=20, k2=6): 570 .. 3,700 touched gallery entries and
+// 1,700 .. 7,800 accumulator updates per query, i.e. ~1 % of the dense work.
+static constexpr int kBlendThreads = 256;
+static constexpr int kBlendPer = 8;        // elements per thread per trip
 static constexpr int kJacSteps = 64;       // V entries of the query row staged per round
-static constexpr int kJacListCap = 3072;   // inverted-list entries staged per round (24 KB)
-static constexpr int kJacMaxTile = 41600;  // fp16 accumulator entries per CTA (81 KB): two CTAs per SM (MSMT17 gallery = 2 tiles)
+static constexpr int kJacMaxTile = 102400; // fp16 accumulator entries per CTA (200 KB): the MSMT17 gallery is one tile
 
-struct JacStage {
-  int64_t b[kJacSteps];        // start of the inverted list of column k_e in the CSC arrays
-  int32_t n[kJacSteps];        // its length
-  int32_t pre[kJacSteps + 1];  // prefix of the lengths inside the round
-  uint16_t v[kJacSteps];       // V[i, k_e]
-  int32_t fit;                 // steps of this round whose lists fit the staging buffer (0: the first list alone is too long)
-  int32_t pad;
-  int32_t own_cnt[kJacThreads];      // staged entries per owner thread (owner = g mod 512)
-  int32_t own_off[kJacThreads + 1];  // their segment in ent[]
-  int32_t scan[33];
-};
-
-__device__ __forceinline__ void jac_apply(__half* acc, int c, uint16_t vg_bits, __half vik) {
-  const __half vg = __ushort_as_half(vg_bits);
-  const __half mn = __hlt(vg, vik) ? vg : vik;
-  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));     // fp16 accumulator, one rounding per add (:87-91)
+__device__ __forceinline__ float jaccard_blend(float a /*temp_min != 0*/, float dn, float lambda_value, __half one_minus_lambda) {
+  const __half den = __float2half_rn(2.0f - a);                                   // 2 - temp_min              (:93)
+  const __half quo = __float2half_rn(a / __half2float(den));                      // temp_min / (2 - temp_min)
+  const __half jac = __float2half_rn(1.0f - __half2float(quo));                   // 1 - ...
+  const __half jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));   // fp16 * fp16(1 - lambda)  (:95)
+  return __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value));                // two roundings, no FMA contraction
 }
 
-// One CTA per query row.  For every non-zero column k of V[i], in ascending k (the reference's accumulation
-// order, :88-92), the gallery rows g of the inverted list of k get  acc[g] = fp16(acc[g] + min(V[i,k], V[g,k])).
-// Only the order per g matters, so every accumulator entry gets an OWNER thread (g mod 512).  Rounds: the
-// offsets of up to 64 steps are staged, their list entries (<= 3072, all loads in flight at once) are bucketed
-// by owner in shared memory, and every thread applies its own few entries in step order -- no barrier per
-// step and no atomics on the accumulator.
-__global__ void __launch_bounds__(kJacThreads)
-k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict__ q_ids, int Qs, int N, int Q, float lambda_value,
-          const float* __restrict__ rowmax,
-          const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
-          const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-          float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
+// final[il, c] = float(fp16(1 - lambda)) + (dist[il, col0 + c] / rowmax[il]) * lambda      (:46,72,95 with temp_min = 0)
+template <bool VEC>
+__global__ void __launch_bounds__(kBlendThreads)
+k_blend_default(const float* __restrict__ dist, int64_t ld, int64_t col0, int Qs, int G, float lambda_value,
+                const float* __restrict__ rowmax, float* __restrict__ final_dist, int64_t ld_final) {
+  const float base = __half2float(__float2half_rn((float)(1.0 - (double)lambda_value)));
+  constexpr int kChunk = kBlendThreads * kBlendPer;
+  const int chunks = (G + kChunk - 1) / kChunk;
+  const int64_t total = (int64_t)Qs * chunks;
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int il = (int)(w / chunks);
+    const int c0 = (int)(w - (int64_t)il * chunks) * kChunk;
+    const float rmax = __ldg(rowmax + il);
+    const float* drow = dist + (int64_t)il * ld + col0;
+    float* orow = final_dist + (int64_t)il * ld_final;
+    if (VEC) {
+      // both rows 16-byte aligned: two float4 per thread, 512 B per warp instruction
+#pragma unroll
+      for (int h = 0; h < kBlendPer / 4; ++h) {
+        const int c = c0 + (h * kBlendThreads + threadIdx.x) * 4;
+        if (c + 4 <= G) {
+          float4 v;
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(drow + c));
+          v.x = __fadd_rn(base, __fmul_rn(v.x / rmax, lambda_value));
+          v.y = __fadd_rn(base, __fmul_rn(v.y / rmax, lambda_value));
+          v.z = __fadd_rn(base, __fmul_rn(v.z / rmax, lambda_value));
+          v.w = __fadd_rn(base, __fmul_rn(v.w / rmax, lambda_value));
+          __stcs(reinterpret_cast<float4*>(orow + c), v);
+        } else {
+          for (int j = c; j < G; ++j) orow[j] = __fadd_rn(base, __fmul_rn(drow[j] / rmax, lambda_value));
+        }
+      }
+    } else {
+      float v[kBlendPer];
+#pragma unroll
+      for (int j = 0; j < kBlendPer; ++j) {
+        const int c = c0 + j * kBlendThreads + threadIdx.x;
+        v[j] = c < G ? __ldg(drow + c) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kBlendPer; ++j) {
+        const int c = c0 + j * kBlendThreads + threadIdx.x;
+        if (c < G) orow[c] = __fadd_rn(base, __fmul_rn(v[j] / rmax, lambda_value));
+      }
+    }
+  }
+}
+
+struct JacStage {
+  int64_t b[kJacSteps];   // start of the inverted list of column k_e in the CSC arrays
+  int32_t n[kJacSteps];   // its length
+  uint16_t v[kJacSteps];  // V[i, k_e]
+};
+
+// One CTA per query row, fp16 accumulator tile for (a tile of) the gallery in shared memory.  The non-zero columns k
+// of V[i] are taken in ascending order (the reference's accumulation order, :88-92): step k adds
+// min(V[i,k], V[g,k]) to acc[g] for every g of the inverted list of k.  Within a step every g occurs once, so the
+// threads share the list freely; steps are separated by a barrier, and each thread already has the list entry of
+// the NEXT step in flight while it applies the current one.  Afterwards only the touched entries are blended and
+// written over the defaults of k_blend_default.
+__global__ void __launch_bounds__(512)
+k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const int32_t* __restrict__ q_ids, int Qs, int N, int Q,
+                 float lambda_value, const float* __restrict__ rowmax,
+                 const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
+                 const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
-  uint64_t* ent = reinterpret_cast<uint64_t*>(smem_raw + sizeof(JacStage));                         // [kJacListCap] row | val << 32
-  __half* acc = reinterpret_cast<__half*>(smem_raw + ((sizeof(JacStage) + kJacListCap * 8 + 15) & ~size_t(15)));   // [tile_cols] temp_min (:87)
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __half* acc = reinterpret_cast<__half*>(smem_raw + ((sizeof(JacStage) + 15) & ~size_t(15)));   // [tile_cols] temp_min (:87)
+  const int tid = threadIdx.x, T = blockDim.x;
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
-  const __half h_one = __float2half_rn(1.f), h_two = __float2half_rn(2.f);
   for (int il = blockIdx.x; il < Qs; il += gridDim.x) {
     const int i = q_ids ? q_ids[il] : il;     // global query index: selects the V row; il selects the distance / output row
     const int len = v_len[i];
     const float rmax = rowmax[il];
-    const float* drow = dist + (int64_t)il * ld + Q;
+    const float* drow = dist + (int64_t)il * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
     for (int t0 = 0; t0 < G; t0 += tile_cols) {
       const int tn = min(tile_cols, G - t0);
-      {
-        uint4* a4 = reinterpret_cast<uint4*>(acc);
-        const int n4 = (tn + 7) >> 3;
-        for (int c = tid; c < n4; c += kJacThreads) a4[c] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      int e0 = 0;
-      while (e0 < len) {
+      const int n8 = (tn + 7) >> 3;
+      uint4* a4 = reinterpret_cast<uint4*>(acc);
+      for (int c = tid; c < n8; c += T) a4[c] = make_uint4(0u, 0u, 0u, 0u);
+      const int gbase = Q + t0;
+      for (int e0 = 0; e0 < len; e0 += kJacSteps) {
         const int nb = min(kJacSteps, len - e0);
-        __syncthreads();   // previous round fully applied (and the zero fill visible) before the stage is rewritten
+        __syncthreads();   // previous round applied (and the zero fill visible) before the stage is rewritten
         if (tid < nb) {
           const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
           const int64_t b = col_off[k];
@@ -455,112 +539,53 @@ k_jaccard(const float* __restrict__ dist, int64_t ld, const int32_t* __restrict_
           st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
         }
         __syncthreads();
-        if (tid == 0) {
-          int run = 0, fit = 0;
-          st.pre[0] = 0;
-          for (int e = 0; e < nb; ++e) {
-            if (run + st.n[e] > kJacListCap) break;
-            run += st.n[e];
-            st.pre[++fit] = run;
-          }
-          st.fit = fit;
-        }
-        __syncthreads();
-        const int fit = st.fit;
-        if (fit == 0) {
-          // a single inverted list longer than the staging buffer: walk it straight from global memory
-          const int n = st.n[0];
-          const int64_t b = st.b[0];
-          const __half vik = __ushort_as_half(st.v[0]);
-          for (int u = lane; u < n; u += 32) {
-            const int g = csc_row[b + u];
-            const int c = g - Q - t0;
-            if (c >= 0 && c < tn && (g & (kJacWarps - 1)) == w) jac_apply(acc, c, csc_val[b + u], vik);
-          }
-          e0 += 1;
-          continue;
-        }
-        // Stage the lists of these steps bucketed by OWNER THREAD (g mod 512): every accumulator entry is only
-        // ever touched by its owner, which applies its few entries in step order -> no barrier, no atomics on acc.
-        const int total = st.pre[fit];
-        st.own_cnt[tid] = 0;
-        __syncthreads();
-        constexpr int kPer = kJacListCap / kJacThreads;   // entries per thread per round
-        uint64_t mine[kPer];
-        int owner[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int idx = tid + j * kJacThreads;
-          owner[j] = -1;
-          if (idx < total) {
-            int lo = 0, hi = fit;                       // step s with pre[s] <= idx < pre[s+1]
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.pre[mid] <= idx) lo = mid; else hi = mid; }
-            const int64_t src = st.b[lo] + (idx - st.pre[lo]);
-            const int g = csc_row[src];
-            const int c = g - Q - t0;
-            if (c >= 0 && c < tn) {
-              owner[j] = g & (kJacThreads - 1);
-              mine[j] = ((uint64_t)lo << 48) | ((uint64_t)csc_val[src] << 32) | (uint32_t)c;   // sorts by step first
-              atomicAdd(&st.own_cnt[owner[j]], 1);
+        // software pipeline over the steps: entry `tid` of step s+1 is loaded before step s is applied
+        int32_t g_nxt = -1; uint16_t w_nxt = 0;
+        if (tid < st.n[0]) { g_nxt = csc_row[st.b[0] + tid]; w_nxt = csc_val[st.b[0] + tid]; }
+        for (int sidx = 0; sidx < nb; ++sidx) {
+          const int32_t g_cur = g_nxt; const uint16_t w_cur = w_nxt;
+          const int n = st.n[sidx];
+          const int64_t b = st.b[sidx];
+          const __half vik = __ushort_as_half(st.v[sidx]);
+          g_nxt = -1;
+          if (sidx + 1 < nb && tid < st.n[sidx + 1]) { g_nxt = csc_row[st.b[sidx + 1] + tid]; w_nxt = csc_val[st.b[sidx + 1] + tid]; }
+          if (g_cur >= 0) {
+            const unsigned c = (unsigned)(g_cur - gbase);
+            if (c < (unsigned)tn) {
+              const __half vg = __ushort_as_half(w_cur);
+              const __half mn = __hlt(vg, vik) ? vg : vik;                                  // np.minimum on fp16  (:90-91)
+              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));           // fp16 accumulator: add in fp32, round once
             }
           }
-        }
-        __syncthreads();
-        {
-          int tot;
-          const int off = block_exclusive_scan(st.own_cnt[tid], st.scan, &tot);
-          st.own_off[tid] = off;
-          if (tid == kJacThreads - 1) st.own_off[kJacThreads] = tot;
-          st.own_cnt[tid] = 0;   // reused as the fill cursor
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < kPer; ++j)
-          if (owner[j] >= 0) ent[st.own_off[owner[j]] + atomicAdd(&st.own_cnt[owner[j]], 1)] = mine[j];
-        __syncthreads();
-        {
-          const int a0 = st.own_off[tid], a1 = st.own_off[tid + 1];
-          for (int x = a0 + 1; x < a1; ++x) {          // insertion sort of a handful of entries by step
-            const uint64_t key = ent[x];
-            int y = x - 1;
-            while (y >= a0 && ent[y] > key) { ent[y + 1] = ent[y]; --y; }
-            ent[y + 1] = key;
+          for (int u = tid + T; u < n; u += T) {   // lists longer than the CTA
+            const unsigned c = (unsigned)(csc_row[b + u] - gbase);
+            if (c < (unsigned)tn) {
+              const __half vg = __ushort_as_half(csc_val[b + u]);
+              const __half mn = __hlt(vg, vik) ? vg : vik;
+              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
+            }
           }
-          for (int x = a0; x < a1; ++x) {
-            const uint64_t en = ent[x];
-            jac_apply(acc, (int)(uint32_t)(en & 0xffffffffu), (uint16_t)((en >> 32) & 0xffffu), __ushort_as_half(st.v[(int)(en >> 48)]));
-          }
+          __syncthreads();   // the next step may hit the same accumulator entries
         }
-        e0 += fit;
       }
-      __syncthreads();
-      // Jaccard + blend, eight independent columns per thread per trip (coalesced 128-byte warp accesses)
-      constexpr int JU = 8;
-      for (int c0 = tid; c0 < tn; c0 += kJacThreads * JU) {
-        float dv[JU];
+      __syncthreads();       // (also covers len == 0: the zero fill is complete)
+      // touched entries only: Jaccard + blend, overwriting the default
+      for (int c8 = tid; c8 < n8; c8 += T) {
+        const uint4 w = a4[c8];
+        if ((w.x | w.y | w.z | w.w) == 0u) continue;
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int j = 0; j < JU; ++j) {
-          const int c = c0 + j * kJacThreads;
-          dv[j] = c < tn ? drow[t0 + c] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < JU; ++j) {
-          const int c = c0 + j * kJacThreads;
-          if (c < tn) {
-            const float a = __half2float(acc[c]);
-            __half jl = one_minus_lambda;   // untouched g (the common case): temp_min = 0 -> jaccard = 1 -> fp16(1 * fp16(1-lambda))
-            if (a != 0.f) {                 // (also keeps 0 / 2 off the slow path of the IEEE division)
-              const __half den = __float2half_rn(__half2float(h_two) - a);            // 2 - temp_min
-              const __half quo = __float2half_rn(a / __half2float(den));              // temp_min / (2 - temp_min)
-              const __half jac = __float2half_rn(__half2float(h_one) - __half2float(quo));  // 1 - ...          (:93)
-              jl = __float2half_rn(__half2float(jac) * __half2float(one_minus_lambda));
-            }
-            const float dn = dv[j] / rmax;                                           // original_dist[i, Q+g]   (:46,72)
-            orow[t0 + c] = __fadd_rn(__half2float(jl), __fmul_rn(dn, lambda_value)); // (:95) two roundings, no FMA contraction
+        for (int j = 0; j < 8; ++j) {
+          const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
+          const int c = c8 * 8 + j;
+          if ((hb & 0x7fffu) != 0 && c < tn) {
+            const float a = __half2float(__ushort_as_half(hb));
+            const float dn = drow[t0 + c] / rmax;                                          // original_dist[i, Q+g]   (:46,72)
+            orow[t0 + c] = jaccard_blend(a, dn, lambda_value, one_minus_lambda);
           }
         }
       }
-      __syncthreads();
+      __syncthreads();       // the tile is zeroed again by the next pass / row
     }
   }
 }
@@ -611,11 +636,11 @@ static int neighbor_count(int k1, int k2) { return (k1 + 1) > k2 ? (k1 + 1) : k2
 extern "C" int mpreid_rerank_neighbor_count(int k1, int k2) { return neighbor_count(k1, k2); }
 extern "C" int mpreid_rerank_v0_capacity(int k1, int64_t N) { return (k1 < 1 || k1 > kMaxK1 || N < 1) ? 0 : v0_capacity(k1, N); }
 
-extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, const int32_t* row_ids, int64_t R, int64_t N,
-                                      int k1, const int32_t* nbr_all, int K, const float* row_max_rows,
-                                      int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream) {
-  MPREID_REQUIRE(dist_rows && nbr_all && row_max_rows && v0_col && v0_val && v0_len, "rerank_build_v0: null pointer");
-  MPREID_REQUIRE(R > 0 && N > 1 && R <= N && N < INT32_MAX && ld_dist >= N, "rerank_build_v0: bad shape R=%lld N=%lld", (long long)R, (long long)N);
+namespace mpreid {
+static int launch_build_v0(const V0Source& src, const int32_t* row_ids, int64_t R, int64_t N, int k1, const int32_t* nbr_all, int K,
+                           const float* row_max_rows, int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, cudaStream_t st) {
+  MPREID_REQUIRE(nbr_all && row_max_rows && v0_col && v0_val && v0_len, "rerank_build_v0: null pointer");
+  MPREID_REQUIRE(R > 0 && N > 1 && R <= N && N < INT32_MAX, "rerank_build_v0: bad shape R=%lld N=%lld", (long long)R, (long long)N);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && K >= k1 + 1, "rerank_build_v0: k1 must be in [1, %d] and K >= k1+1", kMaxK1);
   const int sms = sm_count_of_current_device();
   const int v0_smem = v0_sizes(k1).bytes;
@@ -624,10 +649,32 @@ extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, c
   int v0_ctas = (200 * 1024) / (v0_smem + 1024);
   v0_ctas = v0_ctas > 16 ? 16 : (v0_ctas < 1 ? 1 : v0_ctas);   // 16 x 128 threads fill an SM
   const int64_t grid = R < (int64_t)sms * v0_ctas ? R : (int64_t)sms * v0_ctas;
-  k_build_v0<<<(unsigned)grid, kV0Threads, v0_smem, (cudaStream_t)stream>>>(dist_rows, ld_dist, row_ids, (int)R, k1, K, Keff, nbr_all,
-                                                                            row_max_rows, v0_col, v0_val, v0_len, v0_capacity(k1, N));
+  k_build_v0<<<(unsigned)grid, kV0Threads, v0_smem, st>>>(src, row_ids, (int)R, k1, K, Keff, nbr_all, row_max_rows, v0_col, v0_val, v0_len,
+                                                          v0_capacity(k1, N));
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
+}
+}  // namespace mpreid
+
+extern "C" int mpreid_rerank_build_v0(const float* dist_rows, int64_t ld_dist, const int32_t* row_ids, int64_t R, int64_t N,
+                                      int k1, const int32_t* nbr_all, int K, const float* row_max_rows,
+                                      int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream) {
+  MPREID_REQUIRE(dist_rows && ld_dist >= N, "rerank_build_v0: bad distance rows");
+  V0Source src;
+  memset(&src, 0, sizeof(src));
+  src.dist = dist_rows; src.ld = ld_dist;
+  return launch_build_v0(src, row_ids, R, N, k1, nbr_all, K, row_max_rows, v0_col, v0_val, v0_len, (cudaStream_t)stream);
+}
+
+extern "C" int mpreid_rerank_build_v0_sparse(const int32_t* row_ids, int64_t R, int64_t N, int k1, const int32_t* nbr_all,
+                                             const float* nbr_val_all, int K, const float* row_max_rows,
+                                             const float* xn, int64_t ld_xn, int64_t D, const float* sqnorm,
+                                             int32_t* v0_col, uint16_t* v0_val, int32_t* v0_len, void* stream) {
+  MPREID_REQUIRE(nbr_val_all && xn && sqnorm && D > 0 && ld_xn >= D && D < INT32_MAX, "rerank_build_v0_sparse: bad feature rows");
+  V0Source src;
+  memset(&src, 0, sizeof(src));
+  src.nbr_val = nbr_val_all; src.xn = xn; src.ld_xn = ld_xn; src.D = (int)D; src.sqnorm = sqnorm;
+  return launch_build_v0(src, row_ids, R, N, k1, nbr_all, K, row_max_rows, v0_col, v0_val, v0_len, (cudaStream_t)stream);
 }
 
 extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int k1, int k2) {
@@ -635,13 +682,15 @@ extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int
   return carve_finish(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
 }
 
-extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
-                                    const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
-                                    int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                                    float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_qrows && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
-  MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= N && ld_final >= N - Q,
+namespace mpreid {
+
+// :73-99 for the query rows dist_q[Qs, ...]: dist_q[il, col0 + c] is the distance of query row il to gallery sample c
+static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                              const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
+                              int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                              float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_q && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
+  MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= col0 + (N - Q) && ld_final >= N - Q,
                  "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && k2 >= 1 && k2 <= 64 && K >= neighbor_count(k1, k2), "rerank_finish: bad k1/k2/K");
   MPREID_REQUIRE(((uintptr_t)workspace & 255) == 0, "rerank_finish: workspace must be 256-byte aligned");
@@ -669,21 +718,50 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
   k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, w.C1, w.col_cnt);
   k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
   k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
-  // :84-99
+  // :84-99  dense default, then the sparse accumulation over the touched entries
   const int64_t G = N - Q;
+  {
+    const bool vec = (((uintptr_t)(dist_q + col0) | (uintptr_t)final_dist) & 15) == 0 && ld_dist % 4 == 0 && ld_final % 4 == 0;
+    const int64_t work = Qs * ceil_div(G, kBlendThreads * kBlendPer);
+    const int64_t grid = work < (int64_t)sms * 16 ? work : (int64_t)sms * 16;
+    if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
+    else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
+  }
   const int64_t n_tiles = ceil_div(G, kJacMaxTile);
   int tile_cols = (int)ceil_div(G, n_tiles);
   tile_cols = (tile_cols + 7) & ~7;
-  const int jac_smem = (int)sizeof(JacStage) + kJacListCap * 8 + 16 + tile_cols * 2;
-  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(JacStage) + kJacListCap * 8 + kJacMaxTile * 2 + 32));
-  const int ctas_per_sm = jac_smem <= 54 * 1024 ? 4 : (jac_smem <= 73 * 1024 ? 3 : 2);
+  const int jac_smem = (int)((sizeof(JacStage) + 15) & ~size_t(15)) + tile_cols * 2;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((sizeof(JacStage) + 15) & ~size_t(15)) + kJacMaxTile * 2 + 16));
+  int ctas_per_sm = (225 * 1024) / (jac_smem + 1024);
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+  const int jac_threads = ctas_per_sm >= 4 ? 256 : 512;   // one or two big-tile CTAs per SM: more threads per CTA for the zero / scan sweeps
   const int64_t jac_grid = Qs < (int64_t)sms * ctas_per_sm ? Qs : (int64_t)sms * ctas_per_sm;
-  k_jaccard<<<(unsigned)jac_grid, kJacThreads, jac_smem, st>>>(dist_qrows, ld_dist, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
-                                                               v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                               ld_final, tile_cols);
+  k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
+                                                                      v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                      ld_final, tile_cols);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
+}
+
+}  // namespace mpreid
+
+extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                                    const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
+                                    int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                                    float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
+  return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qrows, ld_dist, Q, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
+                            final_dist, ld_final, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// the same with the query rows given as the [Qs, G] block of query-to-gallery distances alone (column 0 = gallery sample 0):
+// what the fused all-pairs pass keeps of the (Q+G)^2 matrix
+extern "C" int mpreid_rerank_finish_block(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                                          const float* dist_qg, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
+                                          int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                                          float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
+  return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qg, ld_dist, 0, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
+                            final_dist, ld_final, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // single-GPU convenience: neighbours + V0 rows + finish on the whole matrix

@@ -277,6 +277,65 @@ k_row_topk(const float* __restrict__ dist, int64_t ld, int Q, int G, int k, cons
   }
 }
 
+// The same selection over the CANDIDATE LISTS the fused all-pairs pass leaves behind (dist_tc.cu, TopkFuse): row i holds
+// min(cnt[i], cap) unordered entries (column << 32 | fp32 bits) -- every element of the row that is not above thr[i].
+// One warp per row.  status[0] counts rows whose result cannot be trusted (the caller then falls back to the
+// materialising path): the list overflowed, it holds fewer than k entries, or the k-th selected value is not strictly
+// below fl(thr / scale), in which case an element outside the list could tie with it.
+__global__ void __launch_bounds__(kTopkThreads)
+k_cand_topk(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int64_t cand_cap, int N, int k,
+            const float* __restrict__ row_scale, const float* __restrict__ thr,
+            int32_t* __restrict__ idx_out, float* __restrict__ val_out, int32_t* status, int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  WarpSel w;
+  w.q = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * cap;
+  w.hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)warps * cap * 8) + warp * 256;
+  w.lane = lane;
+  const int keff = min(k, N);
+  const int drain_at = cap - kTopkChunk;
+  const bool has_scale = row_scale != nullptr;
+  for (int row_i = blockIdx.x * warps + warp; row_i < N; row_i += gridDim.x * warps) {
+    const float r = has_scale ? row_scale[row_i] : 1.0f;
+    const int cnt_all = cand_cnt[row_i];
+    const int cnt = (int)min((int64_t)cnt_all, cand_cap);
+    const unsigned long long* src = cand + (int64_t)row_i * cand_cap;
+    RowState st;
+    st.count = 0; st.nkeys = 0; st.thr = ~0ull; st.bound = INFINITY;
+    for (int e0 = 0; e0 < cnt; e0 += kTopkChunk) {
+      const int n = min(kTopkChunk, cnt - e0);
+      for (int e = lane; e < n; e += 32) w.q[st.count + e] = src[e0 + e];
+      st.count += n;
+      __syncwarp();
+      if (st.count > drain_at) warp_cut(w, st, keff, r, has_scale);
+    }
+    warp_cut(w, st, keff, r, has_scale);
+    const int P = (int)next_pow2_u32((uint32_t)max(st.count, 1));
+    for (int i = st.count + lane; i < P; i += 32) w.q[i] = ~0ull;
+    __syncwarp();
+    warp_bitonic(w, P);
+    bool bad = cnt_all > cand_cap || st.count < keff;
+    if (!bad && keff > 0) {
+      const float t = has_scale ? thr[row_i] / r : thr[row_i];
+      bad = !((uint32_t)(w.q[keff - 1] >> 32) < order_key(t));
+    }
+    if (bad && lane == 0) atomicAdd(&status[0], 1);
+    if (lane == 0) atomicMax(&status[1], cnt_all);
+    for (int i = lane; i < k; i += 32) {
+      int32_t id = -1;
+      float val = INFINITY;
+      if (i < keff && i < st.count) {
+        id = (int32_t)(w.q[i] & 0xffffffffu);
+        val = order_key_inv((uint32_t)(w.q[i] >> 32));   // the divided value itself (the key is a bijection on non-NaN floats)
+      }
+      idx_out[(int64_t)row_i * k + i] = id;
+      if (val_out) val_out[(int64_t)row_i * k + i] = val;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_row_max(const float* __restrict__ dist, int64_t ld, int Q, int G, float* __restrict__ row_max) {
   __shared__ float sh[8];
@@ -337,6 +396,30 @@ extern "C" int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int
   const int sms = sm_count_of_current_device();
   const int64_t grid = Q < (int64_t)sms * 8 ? Q : (int64_t)sms * 8;
   k_row_max<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dist, ld_dist, (int)Q, (int)G, row_max);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+extern "C" int mpreid_cand_topk(const uint64_t* cand, const int32_t* cand_cnt, int64_t cand_cap, int64_t N, int k,
+                                const float* row_scale, const float* thr, int32_t* idx, float* val, int32_t* status, void* stream) {
+  MPREID_REQUIRE(cand && cand_cnt && thr && idx && status && N > 0 && N < INT32_MAX && cand_cap >= 1, "cand_topk: bad arguments");
+  MPREID_REQUIRE(k >= 1 && k <= kTopkMaxK, "cand_topk: k must be in [1, %d], got %d", kTopkMaxK, k);
+  int cap = (2 * k > 256 ? 2 * k : 256) + kTopkChunk;
+  cap = (cap + 31) / 32 * 32;
+  const int per_warp = cap * 8 + 256 * 4;
+  int warps = (220 * 1024) / per_warp;
+  warps = warps > kTopkWarps ? kTopkWarps : warps;
+  MPREID_REQUIRE(warps >= 1, "cand_topk: k=%d needs more shared memory than one SM has", k);
+  const int smem = warps * per_warp;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_cand_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  MPREID_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));
+  const int sms = sm_count_of_current_device();
+  int ctas_per_sm = (220 * 1024) / (smem + 1024);
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t want = ceil_div(N, warps);
+  const int64_t grid = want < (int64_t)sms * ctas_per_sm ? want : (int64_t)sms * ctas_per_sm;
+  k_cand_topk<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>((const unsigned long long*)cand, cand_cnt, cand_cap, (int)N, k, row_scale, thr,
+                                                                          idx, val, status, cap);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

@@ -370,9 +370,82 @@ def rerank_build_v0(dist_rows: torch.Tensor, row_ids: torch.Tensor | None, N: in
     return v0_col, v0_val, v0_len
 
 
+# ------------------------------------------------------------------------------------------------
+# fused all-pairs pass: top-(k1+1) candidates from the GEMM epilogue, the N x N matrix is never written
+def _operands(x: Prepared, prec: int):
+    if prec == L.X3TF32:
+        return x.hi, x.lo
+    if prec in (L.X3FP16, L.X2FP16):
+        return x.hh, x.hl
+    return x.bf, None
+
+
+def dist_symmetric_topk(x: Prepared, thr: torch.Tensor, cand_cap: int, query_num: int, precision: str | None = None):
+    """utils/reranking.py:36-48 without the matrix: -> (cand int64 [N, cap], cand_cnt int32 [N], block fp32 [Q, G] view,
+    col0 (column of gallery sample 0 in the block's buffer), row_max [N])."""
+    require_cuda()
+    lib = L.load()
+    prec = L.PRECISIONS[(precision or default_precision()).lower()]
+    if prec == L.FP32_SIMT:
+        raise ValueError("the fused all-pairs pass needs a tensor-core precision mode")
+    a, b = _operands(x, prec)
+    if a is None:
+        raise ValueError("features were not prepared for this precision")
+    N, dev = x.n, x.sqnorm.device
+    G = N - query_num
+    lead = query_num & 31
+    ld = (lead + G + 31) // 32 * 32
+    block = torch.empty((query_num, ld), dtype=torch.float32, device=dev)
+    cand = torch.empty((N, cand_cap), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
+    row_max = torch.full((N,), float("-inf"), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_dist_symmetric_topk(_ptr(a), _ptr(b), x.sqnorm.data_ptr(), _ptr(x.hscale), N, x.Dp, x.Dp, prec,
+                                               thr.data_ptr(), cand.data_ptr(), cnt.data_ptr(), cand_cap, query_num,
+                                               block.data_ptr(), ld, row_max.data_ptr(), _stream()), "dist_symmetric_topk")
+    return cand, cnt, block, lead, row_max
+
+
+def cand_topk(cand: torch.Tensor, cnt: torch.Tensor, k: int, row_scale: torch.Tensor | None, thr: torch.Tensor):
+    """-> (idx int32 [N, k], val fp32 [N, k] (divided values), status int32[4] on the device)."""
+    lib = L.load()
+    N, cap = cand.shape
+    dev = cand.device
+    idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+    val = torch.empty((N, k), dtype=torch.float32, device=dev)
+    status = torch.empty((4,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_cand_topk(cand.data_ptr(), cnt.data_ptr(), cap, N, k, _ptr(row_scale), thr.data_ptr(), idx.data_ptr(),
+                                     val.data_ptr(), status.data_ptr(), _stream()), "cand_topk")
+    return idx, val, status
+
+
+def rerank_build_v0_sparse(row_ids: torch.Tensor | None, R: int, N: int, k1: int, nbr_all: torch.Tensor, nbr_val_all: torch.Tensor,
+                           row_max_rows: torch.Tensor, xn: torch.Tensor, sqnorm: torch.Tensor):
+    """utils/reranking.py:51-71 from neighbour lists + values and the feature rows (no matrix rows)."""
+    lib = L.load()
+    C0 = int(lib.mpreid_rerank_v0_capacity(k1, N))
+    if C0 == 0:
+        raise ValueError(f"re_ranking: unsupported k1={k1}")
+    dev = nbr_all.device
+    v0_col = torch.empty((R, C0), dtype=torch.int32, device=dev)
+    v0_val = torch.empty((R, C0), dtype=torch.float16, device=dev)
+    v0_len = torch.empty((R,), dtype=torch.int32, device=dev)
+    assert nbr_all.is_contiguous() and nbr_val_all.is_contiguous() and xn.stride(1) == 1 and xn.dtype == torch.float32
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_rerank_build_v0_sparse(_ptr(row_ids), R, N, k1, nbr_all.data_ptr(), nbr_val_all.data_ptr(), nbr_all.shape[1],
+                                                  row_max_rows.data_ptr(), xn.data_ptr(), xn.stride(0), xn.shape[1], sqnorm.data_ptr(),
+                                                  v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(), _stream()),
+                "rerank_build_v0_sparse")
+    return v0_col, v0_val, v0_len
+
+
 def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor,
-                  N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None) -> torch.Tensor:
-    """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q]."""
+                  N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None,
+                  block_col0: int | None = None) -> torch.Tensor:
+    """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q].
+    block_col0: `dist_qrows` is instead the [Qs, >= col0 + G] buffer of query-to-gallery distances, gallery sample 0 at
+    column block_col0 (what the fused all-pairs pass keeps)."""
     require_cuda()
     lib = L.load()
     v0_col, v0_val, v0_len = v0
@@ -386,8 +459,12 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N
     with torch.cuda.device(dev):
-        L.check(lib.mpreid_rerank_finish(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
-                                         dist_qrows.data_ptr(), dist_qrows.stride(0), _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
-                                         k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, _stream()),
+        if block_col0 is None:
+            fn, base = lib.mpreid_rerank_finish, dist_qrows.data_ptr()
+        else:
+            fn, base = lib.mpreid_rerank_finish_block, dist_qrows.data_ptr() + 4 * block_col0
+        L.check(fn(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
+                   base, dist_qrows.stride(0), _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
+                   k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, _stream()),
                 "rerank_finish")
     return out

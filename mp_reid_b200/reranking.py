@@ -27,12 +27,61 @@ def _all_pairs(prep: E.Prepared, precision=None, row_max: torch.Tensor | None = 
     return E.dist_matrix_all_pairs(prep, precision, out=buf, row_max=row_max)
 
 
+FUSED_MIN_N = 8192        # below this the all-pairs matrix is a few hundred MB and the plain path is as fast
+FUSED_SAMPLE = 2048       # columns sampled for the per-row thresholds
+
+
+def fused_enabled(n: int, precision=None) -> bool:
+    mode = os.environ.get("MPREID_RERANK_FUSED", "auto").lower()
+    if mode in ("0", "off", "no"):
+        return False
+    if (precision or E.default_precision()).lower() in ("simt", "fp32_simt"):
+        return False
+    return mode in ("1", "on", "force") or n >= FUSED_MIN_N
+
+
+def _rerank_fused(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_value: float, precision=None):
+    """utils/reranking.py:36-99 with the (Q+G)^2 matrix kept out of HBM.  Returns (final [Q, G], status int32[4] device):
+    status[0] != 0 means some neighbour list could not be decided from its candidates (use the materialising path).
+
+    1. thresholds: distances of every sample to FUSED_SAMPLE strided columns (one rectangular GEMM, N x 2048), the
+       (K+2)-th smallest per row, padded by 1e-6 * (|x_i|^2 + max |x|^2) -- an upper bound of the K-th smallest of
+       the full row, because the sampled columns are columns of the row;
+    2. symmetric all-pairs GEMM whose epilogue appends every element <= thr to the candidate list of its row (and of
+       its column for mirrored tiles), takes the row maxima and stores only the [Q, G] block;
+    3. top-K of the candidate lists (same keys, same stable order as the streaming top-k over matrix rows);
+    4. V0 rows from neighbour values + feature rows, query expansion, inverted index, Jaccard, blend."""
+    N = prep.n
+    dev = prep.sqnorm.device
+    K = E.rerank_neighbor_count(k1, k2)
+    S = min(N, FUSED_SAMPLE)
+    t = min(K + 2, S)
+    ids = (torch.arange(S, device=dev, dtype=torch.int64) * N) // S
+    smp = prep.take(ids)
+    dS = E.dist_matrix(prep, smp, "sqeuclid", precision)
+    _, sval = E.row_topk(dS, t, None, want_values=True)
+    thr = sval[:, t - 1] + 1e-6 * (prep.sqnorm + prep.sqnorm.max())
+    expect = N * t / S
+    cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))
+    cand, cnt, block, col0, row_max = E.dist_symmetric_topk(prep, thr, cap, query_num, precision)
+    nbr, nbr_val, status = E.cand_topk(cand, cnt, K, row_max, thr)
+    del cand
+    v0 = E.rerank_build_v0_sparse(None, N, N, k1, nbr, nbr_val, row_max, prep.xn, prep.sqnorm)
+    final = E.rerank_finish(nbr, v0, block, None, row_max[:query_num], N, query_num, k1, k2, lambda_value, block_col0=col0)
+    return final, status
+
+
 def _rerank_device(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_value: float, precision=None,
                    local_distmat: torch.Tensor | None = None) -> torch.Tensor:
     if local_distmat is not None:  # :43-44  (orientation: ours is the transpose of the reference's)
         dall = _all_pairs(prep, precision)
         dall.add_(local_distmat.t())
         return E.rerank_from_dist(dall, query_num, k1, k2, lambda_value)
+    if prep.xn is not None and fused_enabled(prep.n, precision):
+        final, status = _rerank_fused(prep, query_num, k1, k2, lambda_value, precision)
+        if int(status[0].item()) == 0:      # one 4-byte read-back at the end of the pipeline
+            return final
+        del final                           # undecided rows (degenerate data: massive ties): take the exact plain path
     row_max = torch.empty((prep.n,), dtype=torch.float32, device=prep.sqnorm.device)
     dall = _all_pairs(prep, precision, row_max)
     return E.rerank_from_dist(dall, query_num, k1, k2, lambda_value, row_max=row_max)
@@ -47,7 +96,7 @@ def re_ranking(probFea, galFea, k1, k2, lambda_value, local_distmat=None, only_l
         return out.cpu().numpy()
     to_dev = lambda x: (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(dev, dtype=torch.float32)
     feat = torch.cat([to_dev(probFea), to_dev(galFea)])
-    prep = E.prep_rows(feat, normalize=False, precision=precision, keep_xn=False)
+    prep = E.prep_rows(feat, normalize=False, precision=precision, keep_xn=True)
     loc = None
     if local_distmat is not None:
         loc = torch.as_tensor(np.asarray(local_distmat), dtype=torch.float32).to(dev)

@@ -353,12 +353,8 @@ def test_two_ranks_on_one_gpu_bit_identical():
     distributed.sharded_evaluator and distributed.rerank_sharded give the one-GPU cmc / mAP / matrices bit for bit.
     Runs on a one-GPU box, so the multi-rank logic is always covered (the check lives in scripts/sharded_eval_check.py)."""
     _run_sharded_check({"MPREID_CHECK_BACKEND": "gloo", "MPREID_CHECK_ONE_DEVICE": "1"})
-
-
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_sharded_evaluator_under_torchrun():
-    """The same check with one rank per GPU over NCCL (gallery slices broadcast over NVLink)."""
-    _run_sharded_check({"MPREID_CHECK_BACKEND": "nccl"})
+    if torch.cuda.device_count() >= 2:   # and with one rank per GPU over NCCL (gallery slices broadcast over NVLink)
+        _run_sharded_check({"MPREID_CHECK_BACKEND": "nccl"})
 
 
 def test_evaluator_reranking_flag(golden_dir, capsys):
@@ -660,11 +656,14 @@ def test_reserved_label_is_rejected():
 
 
 # ------------------------------------------------------------------------------------ round-2 parity holes
-def _rerank_close(got, want, g, tag_mAP, max_abs=1e-3, frac=0.99):
+def _rerank_close(got, want, g, tag_mAP, max_abs=1e-3, frac=0.99, same_tol=0.0):
+    """Element bar of the fp16-emulating mode: every element within max_abs (one fp16 ulp of the Jaccard term), and
+    at least `frac` of them within same_tol (0 when the all-pairs matrix is GIVEN; a few fp32 ulps of the lambda *
+    original_dist term when our GEMM replaces the reference's sgemm)."""
     diff = np.abs(got - want)
     assert got.dtype == np.float32 and got.shape == want.shape
     assert diff.max() <= max_abs, float(diff.max())
-    assert float((diff == 0).mean()) >= frac, float((diff == 0).mean())
+    assert float((diff <= same_tol).mean()) >= frac, float((diff <= same_tol).mean())
     r = orc.rank_eval(got, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
     assert abs(r["mAP"] - g[tag_mAP]) <= 1e-4, (r["mAP"], g[tag_mAP])
 
@@ -695,7 +694,7 @@ def test_re_ranking_local_distmat_matches_reference(golden_dir, prec):
     qn, gn = norm_feats(g)
     local = local_matrix(len(qn) + len(gn))
     fd = reranking.re_ranking(torch.from_numpy(qn), torch.from_numpy(gn), 20, 6, 0.3, local_distmat=local, precision=prec)
-    _rerank_close(fd, g["rrloc_20_6_30_final"], g, "rrloc_20_6_30_mAP", max_abs=1e-3, frac=0.97)
+    _rerank_close(fd, g["rrloc_20_6_30_final"], g, "rrloc_20_6_30_mAP", max_abs=1e-3, frac=0.97, same_tol=1e-6)
     # and it must differ from the run without the local term (the argument is not ignored)
     assert np.abs(fd - g["rr_20_6_30_final"]).max() > 1e-2
 
@@ -722,7 +721,7 @@ def test_sensitive_large_rerank_golden(golden_dir):
     rows = g["rows"]
     diff = np.abs(fd[rows] - g["final_rows"])
     assert diff.max() <= 1e-3, float(diff.max())
-    assert float((diff == 0).mean()) >= 0.97, float((diff == 0).mean())
+    assert float((diff <= 1e-6).mean()) >= 0.97, float((diff <= 1e-6).mean())   # the rest: fp16-ulp flips of the Jaccard term
     rs = fd.astype(np.float64).sum(1)
     assert np.abs(rs - g["row_sums"]).max() <= 1e-5 * np.abs(g["row_sums"]).max()
     assert abs(float(fd.min()) - float(g["final_min"])) <= 1e-3 and abs(float(fd.max()) - float(g["final_max"])) <= 1e-3
@@ -855,3 +854,96 @@ def test_clipstyle_eval_without_any_match_returns_zeros():
     d = rs.rand(6, 80).astype(np.float32)
     cmc, mAP = metrics.clipstyle_eval(d, np.arange(6) + 1000, rs.randint(0, 5, 80), np.zeros(6, np.int64), np.ones(80, np.int64))
     assert mAP == 0.0 and not cmc.any()
+
+
+# ------------------------------------------------------------------------------------ fused all-pairs pass (no N x N matrix)
+def _fused_parts(prep, nq, k1, k2, precision=None):
+    """The fused pass next to the materialising one on the same prepared rows -> dict of both sides' intermediates."""
+    from mp_reid_b200.reranking import FUSED_SAMPLE
+    N = prep.n
+    K = E.rerank_neighbor_count(k1, k2)
+    rm0 = torch.empty(N, device=DEV)
+    dall = E.dist_matrix_all_pairs(prep, precision, row_max=rm0)
+    nbr0, val0 = E.row_topk(dall, K, rm0, want_values=True)
+    S = min(N, FUSED_SAMPLE); t = min(K + 2, S)
+    ids = (torch.arange(S, device=DEV, dtype=torch.int64) * N) // S
+    dS = E.dist_matrix(prep, prep.take(ids), "sqeuclid", precision)
+    _, sval = E.row_topk(dS, t, None, want_values=True)
+    thr = sval[:, t - 1] + 1e-6 * (prep.sqnorm + prep.sqnorm.max())
+    cap = int(min(N, max(256, (int(3 * N * t / S) + 511) // 256 * 256)))
+    cand, cnt, block, col0, rm1 = E.dist_symmetric_topk(prep, thr, cap, nq, precision)
+    nbr1, val1, status = E.cand_topk(cand, cnt, K, rm1, thr)
+    return dict(dall=dall, rm0=rm0, nbr0=nbr0, val0=val0, block=block[:, col0:col0 + N - nq], rm1=rm1, nbr1=nbr1, val1=val1,
+                status=status.cpu().numpy(), cnt=cnt, cap=cap, thr=thr)
+
+
+@pytest.mark.parametrize("prec", ["3xfp16", "3xtf32", "bf16"])
+@pytest.mark.parametrize("shape", [(100, 500, 32, 25, 1.6), (301, 2500, 96, 60, 1.3), (1000, 8100, 256, 300, 2.6)])
+def test_fused_all_pairs_pass_equals_materialised(shape, prec):
+    """The fused pass takes its neighbour lists, row maxima and the [Q, G] block from the SAME accumulators the
+    materialising kernel stores: all three must be bit-identical, and every row decidable (status 0)."""
+    nq, ng, D, n_id, sigma = shape
+    qf, gf, *_ = synth.make_set(nq, ng, D, n_id, 4, seed=31, sigma=sigma)
+    prep = E.prep_rows(torch.cat([qf, gf]).to(DEV), normalize=True, precision=prec)
+    for (k1, k2) in [(20, 6), (7, 1)]:
+        p = _fused_parts(prep, nq, k1, k2, prec)
+        assert p["status"][0] == 0, p["status"]
+        assert int(p["cnt"].max()) <= p["cap"]
+        assert torch.equal(p["rm0"], p["rm1"])
+        assert torch.equal(p["block"], p["dall"][:nq, nq:])
+        assert torch.equal(p["nbr0"], p["nbr1"])
+        assert torch.equal(p["val0"], p["val1"])
+        # the candidate list of a row is exactly the set of row elements not above its threshold
+        d = p["dall"]
+        want_cnt = (d <= p["thr"][:, None]).sum(1).to(torch.int32)
+        assert torch.equal(want_cnt, p["cnt"])
+
+
+def test_fused_rerank_end_to_end_vs_materialised_and_reference(golden_dir, monkeypatch):
+    """re_ranking() through the fused pass: equal to the materialising pipeline except where an expansion member lies
+    outside the neighbour list (its distance is then an fp32 dot product instead of the tensor-core accumulator:
+    last-bit differences -> rare fp16 flips), and inside the reference bars (1e-3 per element, mAP 1e-4)."""
+    g = load(golden_dir, "rerank_small")
+    qn, gn = norm_feats(g)
+    tq, tg = torch.from_numpy(qn), torch.from_numpy(gn)
+    for (k1, k2, lam) in [(20, 6, 0.3), (50, 15, 0.3), (7, 2, 0.5)]:
+        tag = f"rr_{k1}_{k2}_{int(lam * 100)}"
+        monkeypatch.setenv("MPREID_RERANK_FUSED", "0")
+        plain = reranking.re_ranking(tq, tg, k1, k2, lam)
+        monkeypatch.setenv("MPREID_RERANK_FUSED", "1")
+        fused = reranking.re_ranking(tq, tg, k1, k2, lam)
+        diff = np.abs(fused - plain)
+        assert diff.max() <= 1e-3 and float((diff == 0).mean()) >= 0.995, (tag, float(diff.max()), float((diff == 0).mean()))
+        cmc, mAP = metrics.eval_func(fused, g["q_pid"], g["g_pid"], g["q_cam"], g["g_cam"])
+        assert abs(mAP - g[tag + "_mAP"]) <= 1e-4
+        assert np.abs(fused - g[tag + "_final"]).max() <= 1e-3
+    # a larger, noisy set in auto mode (N >= FUSED_MIN_N switches the fused pass on by itself)
+    monkeypatch.delenv("MPREID_RERANK_FUSED")
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_set(1200, 9000, 256, 330, 6, seed=33, sigma=2.4)
+    f = torch.nn.functional.normalize(torch.cat([qf, gf]), dim=1, p=2)
+    assert reranking.fused_enabled(f.shape[0])
+    fused = reranking.re_ranking(f[:1200], f[1200:], 20, 6, 0.3)
+    monkeypatch.setenv("MPREID_RERANK_FUSED", "0")
+    plain = reranking.re_ranking(f[:1200], f[1200:], 20, 6, 0.3)
+    diff = np.abs(fused - plain)
+    assert diff.max() <= 1e-3 and float((diff == 0).mean()) >= 0.995, (float(diff.max()), float((diff == 0).mean()))
+    m1 = metrics.eval_func(fused, q_pid, g_pid, q_cam, g_cam)[1]
+    m0 = metrics.eval_func(plain, q_pid, g_pid, q_cam, g_cam)[1]
+    assert 0.05 < m0 < 0.999 and abs(m1 - m0) <= 2e-5, (m0, m1)
+
+
+def test_fused_rerank_degenerate_input_falls_back(monkeypatch):
+    """Massive ties (many identical rows): thresholds pass everything, candidate lists overflow, status != 0 and
+    re_ranking() silently takes the exact materialising path -- same numbers as with the fused pass switched off."""
+    rs = np.random.RandomState(9)
+    base = rs.randn(6, 64).astype(np.float32)
+    x = torch.from_numpy(base[rs.randint(0, 6, 1500)])              # only 6 distinct rows
+    x = torch.nn.functional.normalize(x, dim=1, p=2)
+    prep = E.prep_rows(x.to(DEV), normalize=False)
+    p = _fused_parts(prep, 200, 20, 6)
+    assert p["status"][0] > 0
+    monkeypatch.setenv("MPREID_RERANK_FUSED", "1")
+    a = reranking.re_ranking(x[:200], x[200:], 20, 6, 0.3)
+    monkeypatch.setenv("MPREID_RERANK_FUSED", "0")
+    b = reranking.re_ranking(x[:200], x[200:], 20, 6, 0.3)
+    assert np.array_equal(a, b)
