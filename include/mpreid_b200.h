@@ -206,12 +206,14 @@ MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                          const float* dist_qrows, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
                          int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                          float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
-/* mpreid_rerank_finish with the query rows given as the [Qs, G] block of query-to-gallery distances alone (column 0 =
- * gallery sample 0, ld_dist >= N-Q): all that the fused all-pairs pass keeps of the (Q+G)^2 matrix (:72,95,99).      */
-MPREID_API int mpreid_rerank_finish_block(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
-                               const float* dist_qg, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
-                               int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                               float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
+/* General form of mpreid_rerank_finish: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the
+ * all-pairs matrix; the pad (Q & 31) for the [Q, G] block mpreid_dist_symmetric_topk keeps; ld_dist >= col0 + N-Q),
+ * and the two halves may run as separate calls on the same workspace: stages 1 = query expansion + inverted index
+ * (:73-82), 2 = Jaccard + blend (:84-99), 3 = both.                                                             */
+MPREID_API int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                            const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
+                            int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                            float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);

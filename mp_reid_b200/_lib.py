@@ -47,7 +47,7 @@ SIGNATURES = {
     "mpreid_dist_symmetric_topk": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "mpreid_cand_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "mpreid_rerank_build_v0_sparse": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
-    "mpreid_rerank_finish_block": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p]),
+    "mpreid_rerank_finish_ex": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _i32, _p]),
     "mpreid_hard_example_mining": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "mpreid_host_average_precision": (C.c_double, [_p, _i32, _i64]),
     "mpreid_host_order_keys": (None, [_p, _i64, _p]),

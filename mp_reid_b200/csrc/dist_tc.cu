@@ -488,18 +488,28 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     unsigned long long* fq_ent = reinterpret_cast<unsigned long long*>(smem_raw + (fq_base - smem_u32(smem_raw))) + (warp - 2) * kFuseQueue;
     int* fq_row = reinterpret_cast<int*>(smem_raw + (fq_base - smem_u32(smem_raw)) + 4 * kFuseQueue * 8) + (warp - 2) * kFuseQueue;
     int fq_count = 0;                                  // warp-uniform
+    // flush: all atomics of the queue are issued before the first dependent store (one memory round trip per flush)
     auto fq_flush = [&]() {
-      for (int e = lane; e < fq_count; e += 32) {
-        const int r = fq_row[e];
-        const int slot = atomicAdd(fuse.cand_cnt + r, 1);
-        if (slot < fuse.cap) fuse.cand[(int64_t)r * fuse.cap + slot] = fq_ent[e];
+      constexpr int kRounds = kFuseQueue / 32;
+      int slot[kRounds];
+#pragma unroll
+      for (int i = 0; i < kRounds; ++i) {
+        const int e = lane + 32 * i;
+        slot[i] = e < fq_count ? atomicAdd(fuse.cand_cnt + fq_row[e], 1) : 0x7fffffff;
+      }
+#pragma unroll
+      for (int i = 0; i < kRounds; ++i) {
+        const int e = lane + 32 * i;
+        if (slot[i] < fuse.cap) fuse.cand[(int64_t)fq_row[e] * fuse.cap + slot[i]] = fq_ent[e];
       }
       __syncwarp();
       fq_count = 0;
     };
-    // append this lane's hits: bit j of mrow = (row_a, col0 + j) qualifies for row row_a; bit j of mcol = it qualifies for
-    // the mirrored row col0 + j (column row_a).  Values are the lane's d[0..32).
-    auto fq_push = [&](uint32_t mrow, uint32_t mcol, int row_a, int col0, const float (&dv)[32]) {
+    // value j of this lane's row in the swizzled staging tile (stage: lane == row, 16-byte chunk c at c ^ (row & 7))
+    auto staged = [&](int j) { return stage[lane * 32 + ((((j >> 2) ^ (lane & 7)) << 2) | (j & 3))]; };
+    // append this lane's hits: bit j of mrow = element (row_a, col0 + j) qualifies for row row_a; bit j of mcol = it
+    // qualifies for the mirrored row col0 + j (column row_a).  The values are read back from the staging tile.
+    auto fq_push = [&](uint32_t mrow, uint32_t mcol, int row_a, int col0) {
       const int n = __popc(mrow) + __popc(mcol);
       int incl = n;
 #pragma unroll
@@ -509,28 +519,29 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       if (total > kFuseQueue) {
         // thresholds that pass (almost) everything: no staging, every lane appends on its own (correct, slow; the
         // candidate lists overflow in this regime anyway and the caller falls back to the materialising path)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {   // (fully unrolled: a dynamic index would move the value array to local memory)
-          if (mrow & (1u << j)) {
-            const int slot = atomicAdd(fuse.cand_cnt + row_a, 1);
-            if (slot < fuse.cap) fuse.cand[(int64_t)row_a * fuse.cap + slot] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(dv[j]);
-          }
-          if (mcol & (1u << j)) {
-            const int slot = atomicAdd(fuse.cand_cnt + col0 + j, 1);
-            if (slot < fuse.cap) fuse.cand[(int64_t)(col0 + j) * fuse.cap + slot] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(dv[j]);
-          }
+        while (mrow) {
+          const int j = __ffs(mrow) - 1; mrow &= mrow - 1;
+          const int slot = atomicAdd(fuse.cand_cnt + row_a, 1);
+          if (slot < fuse.cap) fuse.cand[(int64_t)row_a * fuse.cap + slot] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(staged(j));
+        }
+        while (mcol) {
+          const int j = __ffs(mcol) - 1; mcol &= mcol - 1;
+          const int slot = atomicAdd(fuse.cand_cnt + col0 + j, 1);
+          if (slot < fuse.cap) fuse.cand[(int64_t)(col0 + j) * fuse.cap + slot] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(staged(j));
         }
         return;
       }
       if (fq_count + total > kFuseQueue) fq_flush();
       int pos = fq_count + incl - n;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (mrow & (1u << j)) { fq_ent[pos] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(dv[j]); fq_row[pos] = row_a; ++pos; }
-        if (mcol & (1u << j)) { fq_ent[pos] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(dv[j]); fq_row[pos] = col0 + j; ++pos; }
+      while (mrow) {
+        const int j = __ffs(mrow) - 1; mrow &= mrow - 1;
+        fq_ent[pos] = ((unsigned long long)(uint32_t)(col0 + j) << 32) | __float_as_uint(staged(j)); fq_row[pos] = row_a; ++pos;
+      }
+      while (mcol) {
+        const int j = __ffs(mcol) - 1; mcol &= mcol - 1;
+        fq_ent[pos] = ((unsigned long long)(uint32_t)row_a << 32) | __float_as_uint(staged(j)); fq_row[pos] = col0 + j; ++pos;
       }
       fq_count += total;
-      __syncwarp();
     };
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -591,13 +602,15 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
             }
             // FUSE: only the [Q, G] block is stored (warp-uniform test), shifted so that 32-column groups stay aligned
             const bool store_direct = !FUSE || (gm0 < fuse.keep_rows && gn0 >= fuse.keep_col0);
-            if (store_direct) {
+            if (FUSE || store_direct) {
               // stage: lane == row, 16-byte chunk c of the row goes to position c ^ (row & 7)
 #pragma unroll
               for (int c = 0; c < 8; ++c)
                 *reinterpret_cast<float4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
                     make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
               __syncwarp();
+            }
+            if (store_direct) {
               const int row_lim = FUSE ? min(Q, fuse.keep_rows) : Q;
               const int col_shift = FUSE ? fuse.keep_col0 : 0;
               // drain: 8 lanes cover one 128-byte row, 4 rows per instruction
@@ -618,20 +631,24 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
                   }
                 }
               }
-              __syncwarp();
+              if (!FUSE) __syncwarp();
             }
             if (FUSE) {
-              // candidates: one compare per element and side, hits (about 1 %) go through the warp queue
+              // candidates: two instructions per element and side (set + lop3); the ~1 % hits go through the warp queue
               const uint32_t colmask = gn0 + 32 <= G ? 0xffffffffu : ((1u << (G - gn0)) - 1u);
               uint32_t mrow = 0, mcol = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                mrow |= (d[j] <= thr_r ? 1u : 0u) << j;
-                mcol |= (d[j] <= gthr[cc + j] ? 1u : 0u) << j;
+                uint32_t a, b;
+                asm("set.le.u32.f32 %0, %1, %2;" : "=r"(a) : "f"(d[j]), "f"(thr_r));
+                asm("set.le.u32.f32 %0, %1, %2;" : "=r"(b) : "f"(d[j]), "f"(gthr[cc + j]));
+                mrow |= a & (1u << j);
+                mcol |= b & (1u << j);
               }
               mrow &= colmask;
               mcol = (mirror && row_ok) ? (mcol & colmask) : 0u;
-              fq_push(mrow, mcol, gm, gn0, d);
+              fq_push(mrow, mcol, gm, gn0);
+              __syncwarp();   // the staging tile is rewritten by the next chunk
             }
             if (mirror) {
               // transpose: for a fixed column the 32 lanes hold 32 consecutive rows -> one 128-byte store

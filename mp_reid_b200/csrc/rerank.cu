@@ -14,6 +14,7 @@
 //   k_query_expand  :73-78  V_qe[i] = fp16(mean of the V rows of the first k2 neighbours)
 //   k_csc_*         :80-82  inverted index over gallery rows
 //   k_jaccard       :84-99  fp16 min-accumulation in ascending column order, Jaccard, lambda blend
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mpreid {
@@ -434,7 +435,7 @@ __global__ void k_csc_fill(int N, int Q, const int32_t* __restrict__ v_col, cons
 static constexpr int kBlendThreads = 256;
 static constexpr int kBlendPer = 8;        // elements per thread per trip
 static constexpr int kJacSteps = 64;       // V entries of the query row staged per round
-static constexpr int kJacMaxTile = 102400; // fp16 accumulator entries per CTA (200 KB): the MSMT17 gallery is one tile
+static constexpr int kJacMaxTile = 41600;  // fp16 accumulator entries per CTA (81 KB): two CTAs per SM, the MSMT17 gallery is two tiles
 
 __device__ __forceinline__ float jaccard_blend(float a /*temp_min != 0*/, float dn, float lambda_value, __half one_minus_lambda) {
   const __half den = __float2half_rn(2.0f - a);                                   // 2 - temp_min              (:93)
@@ -492,101 +493,273 @@ k_blend_default(const float* __restrict__ dist, int64_t ld, int64_t col0, int Qs
   }
 }
 
+// ---- warp-per-query variant: the touched entries of one query (a few hundred to a few thousand, see above) live in a
+// per-warp open-addressing hash table in shared memory (gallery index -> fp16 accumulator).  No CTA barrier anywhere:
+// sixteen independent queries per SM overlap their list loads.  The inverted lists of 32 steps are walked as one flat
+// sequence, 32 entries at a time; entries of the same gallery sample inside one group of 32 (they belong to different
+// steps) are applied in lane order == step order, everything else in parallel, so every accumulator sees the
+// reference's order (:88-92).  A query whose table fills up (more than 3/4 of the slots) is handed to the tile
+// kernel through `row_list`.
+static constexpr int kJacHashWarps = 8;
+struct JacWarpStage { int64_t b[32]; int32_t pre[33]; uint16_t v[32]; };
+__host__ __device__ __forceinline__ size_t jac_hash_bytes_per_warp(int H) { return ((size_t)H * 6 + sizeof(JacWarpStage) + 15) & ~size_t(15); }
+
+__global__ void __launch_bounds__(kJacHashWarps * 32)
+k_jaccard_hash(const float* __restrict__ dist, int64_t ld, int64_t col0, const int32_t* __restrict__ q_ids, int Qs, int N, int Q,
+               float lambda_value, const float* __restrict__ rowmax,
+               const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
+               const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
+               float* __restrict__ final_dist, int64_t ld_final, int H, int32_t* __restrict__ row_list, int32_t* __restrict__ row_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* mine = smem_raw + (size_t)warp * jac_hash_bytes_per_warp(H);
+  int32_t* keys = reinterpret_cast<int32_t*>(mine);                       // [H] gallery sample index, -1 = empty
+  uint16_t* accs = reinterpret_cast<uint16_t*>(mine + (size_t)H * 4);     // [H] temp_min (:87), fp16 bits
+  JacWarpStage& st = *reinterpret_cast<JacWarpStage*>(mine + (size_t)H * 6);
+  const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));
+  const unsigned hmask = (unsigned)H - 1u;
+  const int limit = H - (H >> 2);
+  for (int il = blockIdx.x * kJacHashWarps + warp; il < Qs; il += gridDim.x * kJacHashWarps) {
+    const int i = q_ids ? q_ids[il] : il;
+    const int len = v_len[i];
+    {
+      uint4* k4 = reinterpret_cast<uint4*>(keys);
+      for (int c = lane; c < H / 4; c += 32) k4[c] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      uint4* a4 = reinterpret_cast<uint4*>(accs);
+      for (int c = lane; c < H / 8; c += 32) a4[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+    int used = 0;            // warp-uniform
+    bool overflow = false;
+    for (int e0 = 0; e0 < len && !overflow; e0 += 32) {
+      const int nb = min(32, len - e0);
+      int n_l = 0;
+      if (lane < nb) {
+        const int32_t k = v_col[(int64_t)i * C1 + e0 + lane];
+        const int64_t b = col_off[k];
+        n_l = (int)(col_off[k + 1] - b);
+        st.b[lane] = b;
+        st.v[lane] = v_val[(int64_t)i * C1 + e0 + lane];
+      }
+      int incl = n_l;
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      if (lane == 0) st.pre[0] = 0;
+      st.pre[lane + 1] = incl;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
+      // flat walk, two groups of 32 entries in flight
+      for (int x0 = 0; x0 < total && !overflow; x0 += 64) {
+        int32_t gg[2]; uint16_t ww[2], vv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int x = x0 + u * 32 + lane;
+          gg[u] = -1; ww[u] = 0; vv[u] = 0;
+          if (x < total) {
+            int lo = 0, hi = nb;                        // step s with pre[s] <= x < pre[s+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.pre[mid] <= x) lo = mid; else hi = mid; }
+            const int64_t src = st.b[lo] + (x - st.pre[lo]);
+            gg[u] = csc_row[src]; ww[u] = csc_val[src]; vv[u] = st.v[lo];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int32_t g = gg[u];
+          const bool act = g >= 0;
+          // same gallery sample twice in this group: ranks inside the group give the order of application
+          const unsigned peers = __match_any_sync(0xffffffffu, g);
+          const int my = act ? __popc(peers & ((1u << lane) - 1u)) : 0;
+          const int rounds = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
+          for (int r = 0; r < rounds; ++r) {
+            bool fresh = false;
+            if (act && my == r) {
+              unsigned h = ((unsigned)g * 2654435761u) >> 7 & hmask;
+              for (;;) {
+                const int32_t kk = keys[h];
+                if (kk == g) break;
+                if (kk == -1) {
+                  const int32_t old = atomicCAS(&keys[h], -1, g);
+                  if (old == -1) { fresh = true; break; }
+                  if (old == g) break;
+                }
+                h = (h + 1) & hmask;
+              }
+              const __half vg = __ushort_as_half(ww[u]), vik = __ushort_as_half(vv[u]);
+              const __half mn = __hlt(vg, vik) ? vg : vik;                                           // np.minimum on fp16  (:90-91)
+              accs[h] = __half_as_ushort(__float2half_rn(__half2float(__ushort_as_half(accs[h])) + __half2float(mn)));   // (:87-91)
+            }
+            used += __popc(__ballot_sync(0xffffffffu, fresh));
+            __syncwarp();
+          }
+          if (used > limit) overflow = true;    // warp-uniform; the table never gets full, so the probe loops end
+        }
+      }
+      __syncwarp();
+    }
+    if (overflow) {
+      if (lane == 0) row_list[atomicAdd(row_count, 1)] = il;
+      continue;
+    }
+    // touched entries: Jaccard + blend over the default
+    const float rmax = rowmax[il];
+    const float* drow = dist + (int64_t)il * ld + col0;
+    float* orow = final_dist + (int64_t)il * ld_final;
+    for (int h = lane; h < H; h += 32) {
+      const int32_t g = keys[h];
+      const uint16_t hb = accs[h];
+      if (g >= 0 && (hb & 0x7fffu) != 0) {
+        const int c = g - Q;
+        orow[c] = jaccard_blend(__half2float(__ushort_as_half(hb)), drow[c] / rmax, lambda_value, one_minus_lambda);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct JacStage {
-  int64_t b[kJacSteps];   // start of the inverted list of column k_e in the CSC arrays
-  int32_t n[kJacSteps];   // its length
-  uint16_t v[kJacSteps];  // V[i, k_e]
+  int64_t b[kJacSteps];        // start of the inverted list of column k_e in the CSC arrays
+  int32_t n[kJacSteps];        // its length
+  int32_t pre[kJacSteps + 1];  // prefix of the lengths inside the round
+  uint16_t v[kJacSteps];       // V[i, k_e]
+  int32_t fit;                 // steps of this round whose lists fit the entry buffer (0: the first list alone is too long)
+  int32_t pad;
 };
 
-// One CTA per query row, fp16 accumulator tile for (a tile of) the gallery in shared memory.  The non-zero columns k
-// of V[i] are taken in ascending order (the reference's accumulation order, :88-92): step k adds
-// min(V[i,k], V[g,k]) to acc[g] for every g of the inverted list of k.  Within a step every g occurs once, so the
-// threads share the list freely; steps are separated by a barrier, and each thread already has the list entry of
-// the NEXT step in flight while it applies the current one.  Afterwards only the touched entries are blended and
-// written over the defaults of k_blend_default.
+__device__ __forceinline__ void jac_apply(__half* acc, unsigned c, uint16_t vg_bits, __half vik) {
+  const __half vg = __ushort_as_half(vg_bits);
+  const __half mn = __hlt(vg, vik) ? vg : vik;                                  // np.minimum on fp16  (:90-91)
+  acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));           // fp16 accumulator: add in fp32, round once (:87-91)
+}
+
+// Work item = (query row, gallery tile): the CTA keeps an fp16 accumulator for the tile in shared memory.  The non-zero
+// columns k of V[i] are taken in ascending order (the reference's accumulation order, :88-92): step k adds
+// min(V[i,k], V[g,k]) to acc[g] for every g of the inverted list of k.  Rounds of up to 64 steps: the list entries of
+// a round (<= kJacEntries) are first copied to shared memory with every load in flight at once -- walking the lists
+// step by step straight from global memory costs one full memory latency per step -- and then applied step by step;
+// within a step every g occurs once, so the threads share the list freely; steps are separated by a barrier.
+// Afterwards only the touched entries are blended and written over the defaults of k_blend_default.
+static constexpr int kJacEntries = 4096;
+
 __global__ void __launch_bounds__(512)
 k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const int32_t* __restrict__ q_ids, int Qs, int N, int Q,
                  float lambda_value, const float* __restrict__ rowmax,
                  const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
                  const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols) {
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles,
+                 const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
-  __half* acc = reinterpret_cast<__half*>(smem_raw + ((sizeof(JacStage) + 15) & ~size_t(15)));   // [tile_cols] temp_min (:87)
+  int32_t* ent_g = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(JacStage) + 15) & ~size_t(15)));   // [kJacEntries]
+  uint16_t* ent_v = reinterpret_cast<uint16_t*>(ent_g + kJacEntries);                                  // [kJacEntries]
+  __half* acc = reinterpret_cast<__half*>(ent_v + kJacEntries);                                         // [tile_cols] temp_min (:87)
   const int tid = threadIdx.x, T = blockDim.x;
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
-  for (int il = blockIdx.x; il < Qs; il += gridDim.x) {
+  // row_list: only the rows the warp-per-query kernel handed over (their number is known on the device only)
+  const int64_t items = (int64_t)(row_list ? *row_count : Qs) * n_tiles;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ir = (int)(item / n_tiles);
+    const int il = row_list ? row_list[ir] : ir;
+    const int t0 = (int)(item - (int64_t)ir * n_tiles) * tile_cols;
     const int i = q_ids ? q_ids[il] : il;     // global query index: selects the V row; il selects the distance / output row
     const int len = v_len[i];
+    const int tn = min(tile_cols, G - t0);
+    const int n8 = (tn + 7) >> 3;
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    for (int c = tid; c < n8; c += T) a4[c] = make_uint4(0u, 0u, 0u, 0u);
+    const int gbase = Q + t0;
+    int e0 = 0;
+    while (e0 < len) {
+      const int nb = min(kJacSteps, len - e0);
+      __syncthreads();   // previous round applied (and the zero fill visible) before the stage is rewritten
+      if (tid < nb) {
+        const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
+        const int64_t b = col_off[k];
+        st.b[tid] = b;
+        st.n[tid] = (int32_t)(col_off[k + 1] - b);
+        st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // inclusive prefix of the list lengths (two steps per lane), then the number of steps whose lists fit the buffer
+        const int a = 2 * tid < nb ? st.n[2 * tid] : 0, b2 = 2 * tid + 1 < nb ? st.n[2 * tid + 1] : 0;
+        int incl = a + b2;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+        const int before = incl - a - b2;
+        if (tid == 0) st.pre[0] = 0;
+        st.pre[2 * tid + 1] = before + a;
+        if (2 * tid + 2 <= kJacSteps) st.pre[2 * tid + 2] = incl;
+        const unsigned ok0 = __ballot_sync(0xffffffffu, 2 * tid < nb && before + a <= kJacEntries);
+        const unsigned ok1 = __ballot_sync(0xffffffffu, 2 * tid + 1 < nb && incl <= kJacEntries);
+        if (tid == 0) st.fit = __popc(ok0) + __popc(ok1);   // the prefix is monotone: the fitting steps form a leading run
+      }
+      __syncthreads();
+      const int fit = st.fit;
+      if (fit == 0) {
+        // a single inverted list longer than the entry buffer: applied straight from global memory
+        const int n = st.n[0];
+        const int64_t b = st.b[0];
+        const __half vik = __ushort_as_half(st.v[0]);
+        for (int u = tid; u < n; u += T) {
+          const unsigned c = (unsigned)(csc_row[b + u] - gbase);
+          if (c < (unsigned)tn) jac_apply(acc, c, csc_val[b + u], vik);
+        }
+        e0 += 1;
+        continue;
+      }
+      // copy the entries of these steps: four independent (row, value) loads per thread and trip
+      const int total = st.pre[fit];
+      for (int x0 = tid; x0 < total; x0 += 4 * T) {
+        int32_t gg[4]; uint16_t vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = x0 + j * T;
+          gg[j] = -1; vv[j] = 0;
+          if (x < total) {
+            int lo = 0, hi = fit;                       // step s with pre[s] <= x < pre[s+1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.pre[mid] <= x) lo = mid; else hi = mid; }
+            const int64_t src = st.b[lo] + (x - st.pre[lo]);
+            gg[j] = csc_row[src]; vv[j] = csc_val[src];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = x0 + j * T;
+          if (x < total) { ent_g[x] = gg[j]; ent_v[x] = vv[j]; }
+        }
+      }
+      __syncthreads();
+      for (int sidx = 0; sidx < fit; ++sidx) {
+        const __half vik = __ushort_as_half(st.v[sidx]);
+        const int x1 = st.pre[sidx + 1];
+        for (int x = st.pre[sidx] + tid; x < x1; x += T) {
+          const unsigned c = (unsigned)(ent_g[x] - gbase);
+          if (c < (unsigned)tn) jac_apply(acc, c, ent_v[x], vik);
+        }
+        __syncthreads();   // the next step may hit the same accumulator entries
+      }
+      e0 += fit;
+    }
+    __syncthreads();       // (also covers len == 0: the zero fill is complete)
+    // touched entries only: Jaccard + blend, overwriting the default
     const float rmax = rowmax[il];
     const float* drow = dist + (int64_t)il * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
-    for (int t0 = 0; t0 < G; t0 += tile_cols) {
-      const int tn = min(tile_cols, G - t0);
-      const int n8 = (tn + 7) >> 3;
-      uint4* a4 = reinterpret_cast<uint4*>(acc);
-      for (int c = tid; c < n8; c += T) a4[c] = make_uint4(0u, 0u, 0u, 0u);
-      const int gbase = Q + t0;
-      for (int e0 = 0; e0 < len; e0 += kJacSteps) {
-        const int nb = min(kJacSteps, len - e0);
-        __syncthreads();   // previous round applied (and the zero fill visible) before the stage is rewritten
-        if (tid < nb) {
-          const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
-          const int64_t b = col_off[k];
-          st.b[tid] = b;
-          st.n[tid] = (int32_t)(col_off[k + 1] - b);
-          st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
-        }
-        __syncthreads();
-        // software pipeline over the steps: entry `tid` of step s+1 is loaded before step s is applied
-        int32_t g_nxt = -1; uint16_t w_nxt = 0;
-        if (tid < st.n[0]) { g_nxt = csc_row[st.b[0] + tid]; w_nxt = csc_val[st.b[0] + tid]; }
-        for (int sidx = 0; sidx < nb; ++sidx) {
-          const int32_t g_cur = g_nxt; const uint16_t w_cur = w_nxt;
-          const int n = st.n[sidx];
-          const int64_t b = st.b[sidx];
-          const __half vik = __ushort_as_half(st.v[sidx]);
-          g_nxt = -1;
-          if (sidx + 1 < nb && tid < st.n[sidx + 1]) { g_nxt = csc_row[st.b[sidx + 1] + tid]; w_nxt = csc_val[st.b[sidx + 1] + tid]; }
-          if (g_cur >= 0) {
-            const unsigned c = (unsigned)(g_cur - gbase);
-            if (c < (unsigned)tn) {
-              const __half vg = __ushort_as_half(w_cur);
-              const __half mn = __hlt(vg, vik) ? vg : vik;                                  // np.minimum on fp16  (:90-91)
-              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));           // fp16 accumulator: add in fp32, round once
-            }
-          }
-          for (int u = tid + T; u < n; u += T) {   // lists longer than the CTA
-            const unsigned c = (unsigned)(csc_row[b + u] - gbase);
-            if (c < (unsigned)tn) {
-              const __half vg = __ushort_as_half(csc_val[b + u]);
-              const __half mn = __hlt(vg, vik) ? vg : vik;
-              acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(mn));
-            }
-          }
-          __syncthreads();   // the next step may hit the same accumulator entries
-        }
-      }
-      __syncthreads();       // (also covers len == 0: the zero fill is complete)
-      // touched entries only: Jaccard + blend, overwriting the default
-      for (int c8 = tid; c8 < n8; c8 += T) {
-        const uint4 w = a4[c8];
-        if ((w.x | w.y | w.z | w.w) == 0u) continue;
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    for (int c8 = tid; c8 < n8; c8 += T) {
+      const uint4 w = a4[c8];
+      if ((w.x | w.y | w.z | w.w) == 0u) continue;
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
-          const int c = c8 * 8 + j;
-          if ((hb & 0x7fffu) != 0 && c < tn) {
-            const float a = __half2float(__ushort_as_half(hb));
-            const float dn = drow[t0 + c] / rmax;                                          // original_dist[i, Q+g]   (:46,72)
-            orow[t0 + c] = jaccard_blend(a, dn, lambda_value, one_minus_lambda);
-          }
+      for (int j = 0; j < 8; ++j) {
+        const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
+        const int c = c8 * 8 + j;
+        if ((hb & 0x7fffu) != 0 && c < tn) {
+          const float a = __half2float(__ushort_as_half(hb));
+          const float dn = drow[t0 + c] / rmax;                                          // original_dist[i, Q+g]   (:46,72)
+          orow[t0 + c] = jaccard_blend(a, dn, lambda_value, one_minus_lambda);
         }
       }
-      __syncthreads();       // the tile is zeroed again by the next pass / row
     }
+    __syncthreads();       // the tile is zeroed again by the next item
   }
 }
 
@@ -601,6 +774,7 @@ struct FinishWs {
   int32_t* col_cnt; int32_t* col_fill; int64_t* col_off; // [N], [N], [N+1]
   int32_t* csc_row; uint16_t* csc_val;                   // [(N-Q) * C1]
   uint64_t* qe_scratch;                                  // [qe_grid * qe_P]
+  int32_t* jac_rows; int32_t* jac_count;                 // [Q], [1]: query rows handed from the hash kernel to the tile kernel
   int C0; int64_t C1; int qe_grid; int64_t qe_P;
 };
 
@@ -625,6 +799,8 @@ static size_t carve_finish(FinishWs* w, char* base, int64_t N, int64_t Q, int k1
   p = take((size_t)(N - Q) * C1 * 4); if (w) w->csc_row = (int32_t*)p;
   p = take((size_t)(N - Q) * C1 * 2); if (w) w->csc_val = (uint16_t*)p;
   p = take((size_t)qe_grid * qe_P * 8); if (w) w->qe_scratch = (uint64_t*)p;
+  p = take((size_t)Q * 4); if (w) w->jac_rows = (int32_t*)p;
+  p = take(256); if (w) w->jac_count = (int32_t*)p;
   if (w) { w->C0 = C0; w->C1 = C1; w->qe_grid = qe_grid; w->qe_P = qe_P; }
   return off;
 }
@@ -688,8 +864,9 @@ namespace mpreid {
 static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                               const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                               int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                              float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                              float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, cudaStream_t st) {
   MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_q && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
+  MPREID_REQUIRE(stages >= 1 && stages <= 3, "rerank_finish: stages must be 1 (expand + index), 2 (Jaccard + blend) or 3 (both)");
   MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= col0 + (N - Q) && ld_final >= N - Q,
                  "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && k2 >= 1 && k2 <= 64 && K >= neighbor_count(k1, k2), "rerank_finish: bad k1/k2/K");
@@ -704,20 +881,24 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
   carve_finish(&w, (char*)workspace, N, Q, k1, k2, sms);
   const int Keff = (int)(K < N ? K : N);
   const int32_t* v_col = v0_col; const uint16_t* v_val = v0_val; const int32_t* v_len = v0_len;
-  // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
-  if (k2 != 1) {
-    const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
-    k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2 < Keff ? k2 : Keff, nbr_all, v0_col, v0_val, v0_len, w.C0,
-                                                             w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P);
-    v_col = w.v_col; v_val = w.v_val; v_len = w.v_len;
+  if (k2 != 1) { v_col = w.v_col; v_val = w.v_val; v_len = w.v_len; }
+  if (stages & 1) {
+    // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
+    if (k2 != 1) {
+      const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
+      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2 < Keff ? k2 : Keff, nbr_all, v0_col, v0_val, v0_len, w.C0,
+                                                               w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P);
+    }
+    // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
+    k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
+    const int rows_per_cta = 8;
+    const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
+    k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, w.C1, w.col_cnt);
+    k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
+    k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
+    MPREID_CUDA_CHECK(cudaGetLastError());
   }
-  // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
-  k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
-  const int rows_per_cta = 8;
-  const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
-  k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, w.C1, w.col_cnt);
-  k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
-  k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
+  if (!(stages & 2)) return MPREID_OK;
   // :84-99  dense default, then the sparse accumulation over the touched entries
   const int64_t G = N - Q;
   {
@@ -727,19 +908,40 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
     else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
   }
+  // warp-per-query hash kernel first (table sized for the typical touched set); the rows it cannot hold go to the tile kernel
+  const char* jac_env = getenv("MPREID_JACCARD");          // "tile": tile kernel only (tests / comparison)
+  const bool use_hash = !(jac_env && jac_env[0] == 't');
+  const int32_t* row_list = nullptr;
+  if (use_hash) {
+    const int H = w.C1 <= 2048 ? 2048 : 4096;
+    const int hsmem = kJacHashWarps * (int)jac_hash_bytes_per_warp(H);
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
+    MPREID_CUDA_CHECK(cudaMemsetAsync(w.jac_count, 0, sizeof(int32_t), st));
+    int hc = (225 * 1024) / (hsmem + 1024);
+    hc = hc < 1 ? 1 : (hc > 4 ? 4 : hc);
+    const int64_t want = ceil_div(Qs, kJacHashWarps);
+    const int64_t hgrid = want < (int64_t)sms * hc ? want : (int64_t)sms * hc;
+    k_jaccard_hash<<<(unsigned)hgrid, kJacHashWarps * 32, hsmem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
+                                                                      v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                      ld_final, H, w.jac_rows, w.jac_count);
+    row_list = w.jac_rows;
+  }
+  // tile: at most 41,600 gallery entries (81 KB) so that two 512-thread CTAs share an SM at MSMT17 size; a gallery
+  // that needs several tiles is covered by several work items per query (each walks the lists once)
   const int64_t n_tiles = ceil_div(G, kJacMaxTile);
   int tile_cols = (int)ceil_div(G, n_tiles);
   tile_cols = (tile_cols + 7) & ~7;
-  const int jac_smem = (int)((sizeof(JacStage) + 15) & ~size_t(15)) + tile_cols * 2;
-  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((sizeof(JacStage) + 15) & ~size_t(15)) + kJacMaxTile * 2 + 16));
+  const int jac_fixed = (int)((sizeof(JacStage) + 15) & ~size_t(15)) + kJacEntries * 6;
+  const int jac_smem = jac_fixed + tile_cols * 2;
+  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_fixed + kJacMaxTile * 2 + 16));
   int ctas_per_sm = (225 * 1024) / (jac_smem + 1024);
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
-  const int jac_threads = ctas_per_sm >= 4 ? 256 : 512;   // one or two big-tile CTAs per SM: more threads per CTA for the zero / scan sweeps
-  const int64_t jac_grid = Qs < (int64_t)sms * ctas_per_sm ? Qs : (int64_t)sms * ctas_per_sm;
+  const int jac_threads = ctas_per_sm >= 4 ? 256 : 512;
+  const int64_t items = Qs * n_tiles;
+  const int64_t jac_grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
   k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
                                                                       v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                                      ld_final, tile_cols);
+                                                                      ld_final, tile_cols, (int)n_tiles, row_list, w.jac_count);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }
@@ -751,17 +953,19 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                                     int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                                     float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qrows, ld_dist, Q, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, 3, (cudaStream_t)stream);
 }
 
-// the same with the query rows given as the [Qs, G] block of query-to-gallery distances alone (column 0 = gallery sample 0):
-// what the fused all-pairs pass keeps of the (Q+G)^2 matrix
-extern "C" int mpreid_rerank_finish_block(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
-                                          const float* dist_qg, int64_t ld_dist, const int32_t* q_ids, const float* row_max_q,
-                                          int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                                          float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
-  return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qg, ld_dist, 0, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, (cudaStream_t)stream);
+// General form: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the all-pairs matrix, 0 or the
+// alignment pad for the [Qs, G] block the fused all-pairs pass keeps), and the two halves can run as separate calls
+// on the same workspace (stages 1 = query expansion + inverted index, 2 = Jaccard + blend, 3 = both).
+extern "C" int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
+                                       const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
+                                       int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
+                                       float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, void* stream) {
+  MPREID_REQUIRE(col0 >= 0, "rerank_finish_ex: col0 < 0");
+  return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_q, ld_dist, col0, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
+                            final_dist, ld_final, workspace, workspace_bytes, stages, (cudaStream_t)stream);
 }
 
 // single-GPU convenience: neighbours + V0 rows + finish on the whole matrix

@@ -27,6 +27,34 @@ def require_cuda():
         raise RuntimeError("mp_reid_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
 
 
+# Optional stage timeline (bench.py): when `_timeline` is a list, mark(name) appends (name, CUDA event recorded on the
+# current stream); the duration of a stage is the time between its mark and the previous one.
+_timeline = None
+
+
+def timeline_start():
+    global _timeline
+    _timeline = []
+    mark("start")
+
+
+def timeline_stop():
+    """-> [(stage name, ms)] (synchronises)."""
+    global _timeline
+    tl, _timeline = _timeline, None
+    if not tl:
+        return []
+    torch.cuda.synchronize()
+    return [(tl[i][0], tl[i - 1][1].elapsed_time(tl[i][1])) for i in range(1, len(tl))]
+
+
+def mark(name: str):
+    if _timeline is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        _timeline.append((name, ev))
+
+
 def default_precision() -> str:
     return os.environ.get("MPREID_PRECISION", "3xfp16").lower()
 
@@ -179,6 +207,7 @@ def dist_matrix_all_pairs(x: Prepared, precision: str | None = None, out: torch.
     return out
 
 
+RANK_EVAL_LAUNCHES = 8   # kernels one mpreid_rank_eval call launches (6 label-index kernels, rank_count, ap_finalize)
 _RESERVED_LABEL = np.iinfo(np.int64).min   # the empty-slot marker of the label hash table (include/mpreid_b200.h)
 
 
@@ -458,13 +487,12 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
         raise ValueError(f"re_ranking: unsupported arguments N={N} Q={Q} k1={k1} k2={k2}")
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N
+    col0 = Q if block_col0 is None else int(block_col0)
     with torch.cuda.device(dev):
-        if block_col0 is None:
-            fn, base = lib.mpreid_rerank_finish, dist_qrows.data_ptr()
-        else:
-            fn, base = lib.mpreid_rerank_finish_block, dist_qrows.data_ptr() + 4 * block_col0
-        L.check(fn(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
-                   base, dist_qrows.stride(0), _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
-                   k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, _stream()),
-                "rerank_finish")
+        for stages in ((1, 2) if _timeline is not None else (3,)):   # timeline mode: the two halves as separate, timed calls
+            L.check(lib.mpreid_rerank_finish_ex(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
+                                                dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
+                                                k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, stages,
+                                                _stream()), "rerank_finish")
+            mark("rerank.expand_index" if stages == 1 else "rerank.jaccard_blend")
     return out

@@ -61,12 +61,16 @@ def _rerank_fused(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_val
     dS = E.dist_matrix(prep, smp, "sqeuclid", precision)
     _, sval = E.row_topk(dS, t, None, want_values=True)
     thr = sval[:, t - 1] + 1e-6 * (prep.sqnorm + prep.sqnorm.max())
+    E.mark("rerank.thresholds")
     expect = N * t / S
     cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))
     cand, cnt, block, col0, row_max = E.dist_symmetric_topk(prep, thr, cap, query_num, precision)
+    E.mark("rerank.all_pairs_gemm")
     nbr, nbr_val, status = E.cand_topk(cand, cnt, K, row_max, thr)
+    E.mark("rerank.topk")
     del cand
     v0 = E.rerank_build_v0_sparse(None, N, N, k1, nbr, nbr_val, row_max, prep.xn, prep.sqnorm)
+    E.mark("rerank.v0")
     final = E.rerank_finish(nbr, v0, block, None, row_max[:query_num], N, query_num, k1, k2, lambda_value, block_col0=col0)
     return final, status
 

@@ -723,7 +723,10 @@ def test_sensitive_large_rerank_golden(golden_dir):
     assert diff.max() <= 1e-3, float(diff.max())
     assert float((diff <= 1e-6).mean()) >= 0.97, float((diff <= 1e-6).mean())   # the rest: fp16-ulp flips of the Jaccard term
     rs = fd.astype(np.float64).sum(1)
-    assert np.abs(rs - g["row_sums"]).max() <= 1e-5 * np.abs(g["row_sums"]).max()
+    # row sums: a last-bit difference of the row maximum shifts every element by ~1e-7 relative; fp16 flips of the
+    # Jaccard term add 2.4e-4 .. 4.9e-4 each (a V entry that rounds the other way moves every gallery entry sharing it)
+    rel = np.abs(rs - g["row_sums"]) / np.abs(g["row_sums"]).max()
+    assert np.median(rel) <= 1e-6 and rel.max() <= 4e-5, (float(np.median(rel)), float(rel.max()))
     assert abs(float(fd.min()) - float(g["final_min"])) <= 1e-3 and abs(float(fd.max()) - float(g["final_max"])) <= 1e-3
 
 
@@ -936,8 +939,8 @@ def test_fused_rerank_degenerate_input_falls_back(monkeypatch):
     """Massive ties (many identical rows): thresholds pass everything, candidate lists overflow, status != 0 and
     re_ranking() silently takes the exact materialising path -- same numbers as with the fused pass switched off."""
     rs = np.random.RandomState(9)
-    base = rs.randn(6, 64).astype(np.float32)
-    x = torch.from_numpy(base[rs.randint(0, 6, 1500)])              # only 6 distinct rows
+    base = rs.randn(2, 64).astype(np.float32)
+    x = torch.from_numpy(base[rs.randint(0, 2, 1500)])              # only 2 distinct rows: ~750-way ties, more than a list holds
     x = torch.nn.functional.normalize(x, dim=1, p=2)
     prep = E.prep_rows(x.to(DEV), normalize=False)
     p = _fused_parts(prep, 200, 20, 6)
@@ -947,3 +950,20 @@ def test_fused_rerank_degenerate_input_falls_back(monkeypatch):
     monkeypatch.setenv("MPREID_RERANK_FUSED", "0")
     b = reranking.re_ranking(x[:200], x[200:], 20, 6, 0.3)
     assert np.array_equal(a, b)
+
+
+def test_jaccard_hash_kernel_equals_tile_kernel(monkeypatch):
+    """The warp-per-query hash kernel and the tile kernel apply the same fp16 operations in the same per-entry order:
+    bit-identical output, also when the hash tables overflow for some or all rows (noisy sets, large k1 / k2) and those
+    rows are handed to the tile kernel."""
+    for (nq, ng, D, n_id, sigma, k1, k2) in [(300, 2500, 64, 60, 1.2, 20, 6), (400, 6000, 64, 150, 2.6, 20, 6), (200, 3000, 48, 40, 1.5, 50, 15),
+                                             (150, 1200, 32, 30, 1.0, 7, 1)]:
+        qf, gf, *_ = synth.make_set(nq, ng, D, n_id, 4, seed=41, sigma=sigma)
+        prep = E.prep_rows(torch.cat([qf, gf]).to(DEV), normalize=True)
+        rm = torch.empty(prep.n, device=DEV)
+        dall = E.dist_matrix_all_pairs(prep, row_max=rm)
+        monkeypatch.setenv("MPREID_JACCARD", "tile")
+        a = E.rerank_from_dist(dall, nq, k1, k2, 0.3, row_max=rm).clone()
+        monkeypatch.delenv("MPREID_JACCARD")
+        b = E.rerank_from_dist(dall, nq, k1, k2, 0.3, row_max=rm)
+        assert torch.equal(a, b), (nq, ng, k1, k2, float((a - b).abs().max()))
