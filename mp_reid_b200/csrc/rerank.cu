@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kQeThreads)
 k_query_expand(int N, int K, int k2, const int32_t* __restrict__ nbr,
                const int32_t* __restrict__ v0_col, const uint16_t* __restrict__ v0_val, const int32_t* __restrict__ v0_len, int C0,
                int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1,
-               uint64_t* __restrict__ scratch, int64_t scratch_P) {
+               uint64_t* __restrict__ scratch, int64_t scratch_P, int skip_upto) {
   __shared__ uint64_t sbuf[kQeSmemEntries];
   __shared__ int sh[33];
   __shared__ int s_total;
@@ -321,6 +321,7 @@ k_query_expand(int N, int K, int k2, const int32_t* __restrict__ nbr,
     }
     __syncthreads();
     const int T = s_total;
+    if (T <= skip_upto) { __syncthreads(); continue; }   // block-uniform: this row belongs to the warp-per-row kernel
     const int P = (int)next_pow2_u32((uint32_t)max(T, 1));
     uint64_t* buf = (P <= kQeSmemEntries) ? sbuf : scratch + (int64_t)blockIdx.x * scratch_P;
     {
@@ -367,6 +368,93 @@ k_query_expand(int N, int K, int k2, const int32_t* __restrict__ nbr,
     }
     if (tid == 0) v_len[i] = written;
     __syncthreads();
+  }
+}
+
+// Warp-per-row variant for the common case (the k2 gathered V0 rows hold at most kQeWarpEntries entries together, e.g.
+// 6 x ~25 for k1 = 20, k2 = 6): gather, warp-level bitonic sort by (column, m), segment sums.  No CTA barrier; eight
+// rows in flight per CTA.  Rows with more entries are left to k_query_expand (skip_upto).
+static constexpr int kQeWarpEntries = 512;
+static constexpr int kQeWarps = 8;
+
+__global__ void __launch_bounds__(kQeWarps * 32)
+k_query_expand_warp(int N, int K, int k2, const int32_t* __restrict__ nbr,
+                    const int32_t* __restrict__ v0_col, const uint16_t* __restrict__ v0_val, const int32_t* __restrict__ v0_len, int C0,
+                    int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1) {
+  __shared__ uint64_t sbuf[kQeWarps][kQeWarpEntries];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* buf = sbuf[warp];
+  const float cnt = (float)k2;
+  for (int i = blockIdx.x * kQeWarps + warp; i < N; i += gridDim.x * kQeWarps) {
+    // lane m (< k2 <= 64: two rows per lane) holds neighbour m and the length of its V0 row
+    int32_t r[2]; int len[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = lane + 32 * h;
+      r[h] = m < k2 ? nbr[(int64_t)i * K + m] : -1;
+      len[h] = r[h] >= 0 ? v0_len[r[h]] : 0;
+    }
+    int incl0 = len[0];
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl0, o); if (lane >= o) incl0 += y; }
+    const int tot0 = __shfl_sync(0xffffffffu, incl0, 31);
+    int incl1 = len[1];
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl1, o); if (lane >= o) incl1 += y; }
+    const int T = tot0 + __shfl_sync(0xffffffffu, incl1, 31);
+    if (T > kQeWarpEntries) continue;                    // warp-uniform: the CTA kernel takes this row
+    // gather (col, m, val): key = col << 32 | m << 16 | fp16 bits
+    for (int m = 0; m < k2; ++m) {
+      const int h = m >> 5, src = m & 31;
+      const int32_t rm = __shfl_sync(0xffffffffu, r[h], src);
+      const int lm = __shfl_sync(0xffffffffu, len[h], src);
+      const int base = (h ? tot0 : 0) + __shfl_sync(0xffffffffu, (h ? incl1 : incl0) - len[h], src);
+      for (int e = lane; e < lm; e += 32) {
+        const uint64_t col = (uint32_t)v0_col[(int64_t)rm * C0 + e];
+        buf[base + e] = (col << 32) | ((uint64_t)m << 16) | v0_val[(int64_t)rm * C0 + e];
+      }
+    }
+    const int P = (int)next_pow2_u32((uint32_t)max(T, 1));
+    for (int t = T + lane; t < P; t += 32) buf[t] = ~0ull;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (P >> 1); t += 32) {      // compare-exchange pair t of this stage: every lane works
+          const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+          const uint64_t x = buf[lo], y = buf[hi];
+          const bool up = (lo & kk) == 0;
+          if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
+        }
+        __syncwarp();
+      }
+    }
+    // segment heads sum their (<= k2) members in m order, fp32, then / k2 -> fp16   (:76)
+    int written = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      bool keep = false;
+      uint16_t hv = 0;
+      int32_t col = 0;
+      if (t < T) {
+        const uint64_t key = buf[t];
+        col = (int32_t)(key >> 32);
+        const bool head = (t == 0) || ((int32_t)(buf[t - 1] >> 32) != col);
+        if (head) {
+          float sum = __half2float(__ushort_as_half((uint16_t)(key & 0xffff)));
+          for (int u = t + 1; u < T && (int32_t)(buf[u] >> 32) == col; ++u)
+            sum += __half2float(__ushort_as_half((uint16_t)(buf[u] & 0xffff)));
+          hv = __half_as_ushort(__float2half_rn(sum / cnt));
+          keep = (hv & 0x7fff) != 0;
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int pos = written + __popc(bal & ((1u << lane) - 1u));
+        v_col[(int64_t)i * C1 + pos] = col;
+        v_val[(int64_t)i * C1 + pos] = hv;
+      }
+      written += __popc(bal);
+    }
+    if (lane == 0) v_len[i] = written;
+    __syncwarp();
   }
 }
 
@@ -493,128 +581,187 @@ k_blend_default(const float* __restrict__ dist, int64_t ld, int64_t col0, int Qs
   }
 }
 
-// ---- warp-per-query variant: the touched entries of one query (a few hundred to a few thousand, see above) live in a
-// per-warp open-addressing hash table in shared memory (gallery index -> fp16 accumulator).  No CTA barrier anywhere:
-// sixteen independent queries per SM overlap their list loads.  The inverted lists of 32 steps are walked as one flat
-// sequence, 32 entries at a time; entries of the same gallery sample inside one group of 32 (they belong to different
-// steps) are applied in lane order == step order, everything else in parallel, so every accumulator sees the
-// reference's order (:88-92).  A query whose table fills up (more than 3/4 of the slots) is handed to the tile
-// kernel through `row_list`.
-static constexpr int kJacHashWarps = 8;
-struct JacWarpStage { int64_t b[32]; int32_t pre[33]; uint16_t v[32]; };
-__host__ __device__ __forceinline__ size_t jac_hash_bytes_per_warp(int H) { return ((size_t)H * 6 + sizeof(JacWarpStage) + 15) & ~size_t(15); }
+// ---- k_jaccard_bucket: the production kernel.  Work item = (query row, gallery tile) as in k_jaccard_sparse below,
+// but without a barrier per step (measured at the MSMT17 shape: ~150 steps and ~26,000 accumulator updates per query;
+// with one or two resident CTAs per SM the per-step barriers and a binary search per entry cost 4.2 ms).
+// The flat sequence of list entries (step-major == the reference's accumulation order) is cut into rounds of
+// <= kJacRound entries.  Per round:
+//   A. every warp takes a contiguous 1/16 of the round (16 entries per lane, kept in registers), forms
+//      min(V[i,k], V[g,k]) and counts its entries per OWNER warp (the tile is split into 16 contiguous ranges);
+//   B. exact offsets: bucket of owner o = the entries of producer 0, then producer 1, ...: global step order is kept;
+//   C. the producers scatter from registers into the buckets;
+//   D. every owner warp applies its bucket 32 entries at a time; entries of the same gallery sample inside one group
+//      (different steps) go in lane order, everything else in parallel.
+// Four barriers per round instead of one per step; every entry is read from global memory once per tile.
+static constexpr int kJacRound = 8192;
+static constexpr int kJacBWarps = 16;
+static constexpr int kJacPerLane = kJacRound / (kJacBWarps * 32);   // 16
 
-__global__ void __launch_bounds__(kJacHashWarps * 32)
-k_jaccard_hash(const float* __restrict__ dist, int64_t ld, int64_t col0, const int32_t* __restrict__ q_ids, int Qs, int N, int Q,
-               float lambda_value, const float* __restrict__ rowmax,
-               const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
-               const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-               float* __restrict__ final_dist, int64_t ld_final, int H, int32_t* __restrict__ row_list, int32_t* __restrict__ row_count) {
+struct JacBStage {
+  int64_t b[kJacSteps];
+  int32_t pre[kJacSteps + 1];
+  uint16_t v[kJacSteps];
+  int32_t cnt[kJacBWarps][kJacBWarps];    // [producer][owner]
+  int32_t off[kJacBWarps][kJacBWarps];    // [producer][owner] start inside the entry buffer
+  int32_t obase[kJacBWarps + 1];          // bucket boundaries
+};
+
+__global__ void __launch_bounds__(kJacBWarps * 32)
+k_jaccard_bucket(const float* __restrict__ dist, int64_t ld, int64_t col0, const int32_t* __restrict__ q_ids, int Qs, int N, int Q,
+                 float lambda_value, const float* __restrict__ rowmax,
+                 const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
+                 const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* mine = smem_raw + (size_t)warp * jac_hash_bytes_per_warp(H);
-  int32_t* keys = reinterpret_cast<int32_t*>(mine);                       // [H] gallery sample index, -1 = empty
-  uint16_t* accs = reinterpret_cast<uint16_t*>(mine + (size_t)H * 4);     // [H] temp_min (:87), fp16 bits
-  JacWarpStage& st = *reinterpret_cast<JacWarpStage*>(mine + (size_t)H * 6);
+  JacBStage& st = *reinterpret_cast<JacBStage*>(smem_raw);
+  int32_t* ent_c = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(JacBStage) + 15) & ~size_t(15)));   // [kJacRound] column inside the tile
+  uint16_t* ent_m = reinterpret_cast<uint16_t*>(ent_c + kJacRound);                                     // [kJacRound] min(V[i,k], V[g,k])
+  __half* acc = reinterpret_cast<__half*>(ent_m + kJacRound);                                           // [tile_cols] temp_min (:87)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));
-  const unsigned hmask = (unsigned)H - 1u;
-  const int limit = H - (H >> 2);
-  for (int il = blockIdx.x * kJacHashWarps + warp; il < Qs; il += gridDim.x * kJacHashWarps) {
+  const int64_t items = (int64_t)Qs * n_tiles;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int il = (int)(item / n_tiles);
+    const int t0 = (int)(item - (int64_t)il * n_tiles) * tile_cols;
     const int i = q_ids ? q_ids[il] : il;
     const int len = v_len[i];
-    {
-      uint4* k4 = reinterpret_cast<uint4*>(keys);
-      for (int c = lane; c < H / 4; c += 32) k4[c] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      uint4* a4 = reinterpret_cast<uint4*>(accs);
-      for (int c = lane; c < H / 8; c += 32) a4[c] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncwarp();
-    int used = 0;            // warp-uniform
-    bool overflow = false;
-    for (int e0 = 0; e0 < len && !overflow; e0 += 32) {
-      const int nb = min(32, len - e0);
+    const int tn = min(tile_cols, G - t0);
+    const int n8 = (tn + 7) >> 3;
+    const float own_scale = (float)kJacBWarps / (float)tn;
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    for (int c = tid; c < n8; c += kJacBWarps * 32) a4[c] = make_uint4(0u, 0u, 0u, 0u);
+    const int gbase = Q + t0;
+    for (int e0 = 0; e0 < len; e0 += kJacSteps) {
+      const int nb = min(kJacSteps, len - e0);
+      __syncthreads();   // previous stage fully consumed (and the zero fill visible)
       int n_l = 0;
-      if (lane < nb) {
-        const int32_t k = v_col[(int64_t)i * C1 + e0 + lane];
-        const int64_t b = col_off[k];
-        n_l = (int)(col_off[k + 1] - b);
-        st.b[lane] = b;
-        st.v[lane] = v_val[(int64_t)i * C1 + e0 + lane];
-      }
-      int incl = n_l;
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-      if (lane == 0) st.pre[0] = 0;
-      st.pre[lane + 1] = incl;
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      __syncwarp();
-      // flat walk, two groups of 32 entries in flight
-      for (int x0 = 0; x0 < total && !overflow; x0 += 64) {
-        int32_t gg[2]; uint16_t ww[2], vv[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int x = x0 + u * 32 + lane;
-          gg[u] = -1; ww[u] = 0; vv[u] = 0;
-          if (x < total) {
-            int lo = 0, hi = nb;                        // step s with pre[s] <= x < pre[s+1]
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.pre[mid] <= x) lo = mid; else hi = mid; }
-            const int64_t src = st.b[lo] + (x - st.pre[lo]);
-            gg[u] = csc_row[src]; ww[u] = csc_val[src]; vv[u] = st.v[lo];
-          }
+      if (tid < kJacSteps) {
+        if (tid < nb) {
+          const int32_t k = v_col[(int64_t)i * C1 + e0 + tid];
+          const int64_t b = col_off[k];
+          n_l = (int)(col_off[k + 1] - b);
+          st.b[tid] = b;
+          st.v[tid] = v_val[(int64_t)i * C1 + e0 + tid];
         }
+        // inclusive prefix over the 64 steps (two warps)
+        int incl = n_l;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        st.pre[tid + 1] = incl;                                  // second warp: corrected below by the total of the first
+        if (tid == 0) st.pre[0] = 0;
+      }
+      __syncthreads();
+      const int first32 = st.pre[32];
+      if (tid >= 32 && tid < kJacSteps) st.pre[tid + 1] += first32;
+      __syncthreads();
+      const int total = st.pre[nb];
+      for (int r0 = 0; r0 < total; r0 += kJacRound) {
+        const int rn = min(kJacRound, total - r0);
+        // ---- A: this warp's contiguous share of the round, in registers
+        const int per_warp = (rn + kJacBWarps - 1) / kJacBWarps;
+        const int w0 = warp * per_warp, w1 = min(rn, w0 + per_warp);
+        int32_t ec[kJacPerLane]; uint16_t em[kJacPerLane]; int8_t eo[kJacPerLane];
+        for (int o = lane; o < kJacBWarps; o += 32) st.cnt[warp][o] = 0;
+        __syncwarp();
+        int step = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int32_t g = gg[u];
-          const bool act = g >= 0;
-          // same gallery sample twice in this group: ranks inside the group give the order of application
-          const unsigned peers = __match_any_sync(0xffffffffu, g);
-          const int my = act ? __popc(peers & ((1u << lane) - 1u)) : 0;
-          const int rounds = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
-          for (int r = 0; r < rounds; ++r) {
-            bool fresh = false;
-            if (act && my == r) {
-              unsigned h = ((unsigned)g * 2654435761u) >> 7 & hmask;
-              for (;;) {
-                const int32_t kk = keys[h];
-                if (kk == g) break;
-                if (kk == -1) {
-                  const int32_t old = atomicCAS(&keys[h], -1, g);
-                  if (old == -1) { fresh = true; break; }
-                  if (old == g) break;
-                }
-                h = (h + 1) & hmask;
-              }
-              const __half vg = __ushort_as_half(ww[u]), vik = __ushort_as_half(vv[u]);
-              const __half mn = __hlt(vg, vik) ? vg : vik;                                           // np.minimum on fp16  (:90-91)
-              accs[h] = __half_as_ushort(__float2half_rn(__half2float(__ushort_as_half(accs[h])) + __half2float(mn)));   // (:87-91)
+        for (int it = 0; it < kJacPerLane; ++it) {
+          const int x = w0 + it * 32 + lane;
+          ec[it] = -1; em[it] = 0; eo[it] = -1;
+          if (x < w1) {
+            const int xf = r0 + x;
+            while (st.pre[step + 1] <= xf) ++step;             // monotone in it: amortised O(1)
+            const int64_t src = st.b[step] + (xf - st.pre[step]);
+            const unsigned c = (unsigned)(csc_row[src] - gbase);
+            if (c < (unsigned)tn) {
+              const __half vg = __ushort_as_half(csc_val[src]), vik = __ushort_as_half(st.v[step]);
+              em[it] = __half_as_ushort(__hlt(vg, vik) ? vg : vik);                        // np.minimum on fp16  (:90-91)
+              ec[it] = (int32_t)c;
+              eo[it] = (int8_t)min(kJacBWarps - 1, (int)((float)c * own_scale));
             }
-            used += __popc(__ballot_sync(0xffffffffu, fresh));
-            __syncwarp();
           }
-          if (used > limit) overflow = true;    // warp-uniform; the table never gets full, so the probe loops end
         }
+#pragma unroll
+        for (int it = 0; it < kJacPerLane; ++it) {
+          const int o = eo[it];
+          const unsigned peers = __match_any_sync(0xffffffffu, o);
+          if (o >= 0 && (peers & ((1u << lane) - 1u)) == 0) st.cnt[warp][o] += __popc(peers);   // group leader; one leader per owner
+          __syncwarp();
+        }
+        __syncthreads();
+        // ---- B: offsets  off[p][o] = sum_{o' < o} total[o'] + sum_{p' < p} cnt[p'][o]
+        if (tid < kJacBWarps) {
+          int tot = 0;
+          for (int p = 0; p < kJacBWarps; ++p) { st.off[p][tid] = tot; tot += st.cnt[p][tid]; }
+          int incl = tot;
+          for (int o = 1; o < kJacBWarps; o <<= 1) { const int y = __shfl_up_sync(0x0000ffffu, incl, o); if (lane >= o) incl += y; }
+          st.obase[tid + 1] = incl;
+          if (tid == 0) st.obase[0] = 0;
+          const int before = incl - tot;
+          for (int p = 0; p < kJacBWarps; ++p) st.off[p][tid] += before;
+        }
+        __syncthreads();
+        // ---- C: scatter (same grouping as in A, so ranks inside a group are the lane order)
+#pragma unroll
+        for (int it = 0; it < kJacPerLane; ++it) {
+          const int o = eo[it];
+          const unsigned peers = __match_any_sync(0xffffffffu, o);
+          if (o >= 0) {
+            const int pos = st.off[warp][o] + __popc(peers & ((1u << lane) - 1u));
+            ent_c[pos] = ec[it]; ent_m[pos] = em[it];
+          }
+          __syncwarp();
+          if (o >= 0 && (peers & ((1u << lane) - 1u)) == 0) st.off[warp][o] += __popc(peers);
+          __syncwarp();
+        }
+        __syncthreads();
+        // ---- D: owner warps apply their buckets in order
+        {
+          const int x1 = st.obase[warp + 1];
+          for (int x0 = st.obase[warp]; x0 < x1; x0 += 32) {
+            const int x = x0 + lane;
+            const bool act = x < x1;
+            const int32_t c = act ? ent_c[x] : -1 - lane;       // inactive lanes: distinct dummies
+            const uint16_t m = act ? ent_m[x] : 0;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            const int my = __popc(peers & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
+            for (int r = 0; r < rounds; ++r) {
+              if (act && my == r)
+                acc[c] = __float2half_rn(__half2float(acc[c]) + __half2float(__ushort_as_half(m)));   // fp16 accumulator (:87-91)
+              __syncwarp();
+            }
+          }
+        }
+        __syncthreads();   // buckets consumed before the next round rewrites them
       }
-      __syncwarp();
     }
-    if (overflow) {
-      if (lane == 0) row_list[atomicAdd(row_count, 1)] = il;
-      continue;
-    }
-    // touched entries: Jaccard + blend over the default
+    __syncthreads();       // (also covers len == 0: the zero fill is complete)
+    // touched entries only: Jaccard + blend, overwriting the default
     const float rmax = rowmax[il];
     const float* drow = dist + (int64_t)il * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
-    for (int h = lane; h < H; h += 32) {
-      const int32_t g = keys[h];
-      const uint16_t hb = accs[h];
-      if (g >= 0 && (hb & 0x7fffu) != 0) {
-        const int c = g - Q;
-        orow[c] = jaccard_blend(__half2float(__ushort_as_half(hb)), drow[c] / rmax, lambda_value, one_minus_lambda);
+    for (int c8 = tid; c8 < n8; c8 += kJacBWarps * 32) {
+      const uint4 w = a4[c8];
+      if ((w.x | w.y | w.z | w.w) == 0u) continue;
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
+        const int c = c8 * 8 + j;
+        if ((hb & 0x7fffu) != 0 && c < tn) {
+          const float a = __half2float(__ushort_as_half(hb));
+          const float dn = drow[t0 + c] / rmax;                                          // original_dist[i, Q+g]   (:46,72)
+          orow[t0 + c] = jaccard_blend(a, dn, lambda_value, one_minus_lambda);
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();       // the tile is zeroed again by the next item
   }
 }
 
+// ---- k_jaccard_sparse: the straightforward variant (a barrier per step), kept as the in-tree cross-check of the bucket
+// kernel (MPREID_JACCARD=tile; tests compare the two bit for bit).
 struct JacStage {
   int64_t b[kJacSteps];        // start of the inverted list of column k_e in the CSC arrays
   int32_t n[kJacSteps];        // its length
@@ -644,8 +791,7 @@ k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const
                  float lambda_value, const float* __restrict__ rowmax,
                  const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
                  const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles,
-                 const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
   int32_t* ent_g = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(JacStage) + 15) & ~size_t(15)));   // [kJacEntries]
@@ -654,12 +800,10 @@ k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const
   const int tid = threadIdx.x, T = blockDim.x;
   const int G = N - Q;
   const __half one_minus_lambda = __float2half_rn((float)(1.0 - (double)lambda_value));  // fp16(1 - lambda)  (:95)
-  // row_list: only the rows the warp-per-query kernel handed over (their number is known on the device only)
-  const int64_t items = (int64_t)(row_list ? *row_count : Qs) * n_tiles;
+  const int64_t items = (int64_t)Qs * n_tiles;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int ir = (int)(item / n_tiles);
-    const int il = row_list ? row_list[ir] : ir;
-    const int t0 = (int)(item - (int64_t)ir * n_tiles) * tile_cols;
+    const int il = (int)(item / n_tiles);
+    const int t0 = (int)(item - (int64_t)il * n_tiles) * tile_cols;
     const int i = q_ids ? q_ids[il] : il;     // global query index: selects the V row; il selects the distance / output row
     const int len = v_len[i];
     const int tn = min(tile_cols, G - t0);
@@ -774,7 +918,6 @@ struct FinishWs {
   int32_t* col_cnt; int32_t* col_fill; int64_t* col_off; // [N], [N], [N+1]
   int32_t* csc_row; uint16_t* csc_val;                   // [(N-Q) * C1]
   uint64_t* qe_scratch;                                  // [qe_grid * qe_P]
-  int32_t* jac_rows; int32_t* jac_count;                 // [Q], [1]: query rows handed from the hash kernel to the tile kernel
   int C0; int64_t C1; int qe_grid; int64_t qe_P;
 };
 
@@ -799,8 +942,6 @@ static size_t carve_finish(FinishWs* w, char* base, int64_t N, int64_t Q, int k1
   p = take((size_t)(N - Q) * C1 * 4); if (w) w->csc_row = (int32_t*)p;
   p = take((size_t)(N - Q) * C1 * 2); if (w) w->csc_val = (uint16_t*)p;
   p = take((size_t)qe_grid * qe_P * 8); if (w) w->qe_scratch = (uint64_t*)p;
-  p = take((size_t)Q * 4); if (w) w->jac_rows = (int32_t*)p;
-  p = take(256); if (w) w->jac_count = (int32_t*)p;
   if (w) { w->C0 = C0; w->C1 = C1; w->qe_grid = qe_grid; w->qe_P = qe_P; }
   return off;
 }
@@ -885,9 +1026,14 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
   if (stages & 1) {
     // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
     if (k2 != 1) {
+      // rows whose k2 gathered V0 rows hold <= 512 entries: one warp each; the rest (large k1 / k2): one CTA each
+      const int k2e = k2 < Keff ? k2 : Keff;
+      const int64_t wgrid = ceil_div(N, kQeWarps) < (int64_t)sms * 6 ? ceil_div(N, kQeWarps) : (int64_t)sms * 6;
+      k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, w.C0,
+                                                                   w.v_col, w.v_val, w.v_len, w.C1);
       const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
-      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2 < Keff ? k2 : Keff, nbr_all, v0_col, v0_val, v0_len, w.C0,
-                                                               w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P);
+      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, w.C0,
+                                                               w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P, kQeWarpEntries);
     }
     // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
     k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
@@ -908,40 +1054,42 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
     else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
   }
-  // warp-per-query hash kernel first (table sized for the typical touched set); the rows it cannot hold go to the tile kernel
-  const char* jac_env = getenv("MPREID_JACCARD");          // "tile": tile kernel only (tests / comparison)
-  const bool use_hash = !(jac_env && jac_env[0] == 't');
-  const int32_t* row_list = nullptr;
-  if (use_hash) {
-    const int H = w.C1 <= 2048 ? 2048 : 4096;
-    const int hsmem = kJacHashWarps * (int)jac_hash_bytes_per_warp(H);
-    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
-    MPREID_CUDA_CHECK(cudaMemsetAsync(w.jac_count, 0, sizeof(int32_t), st));
-    int hc = (225 * 1024) / (hsmem + 1024);
-    hc = hc < 1 ? 1 : (hc > 4 ? 4 : hc);
-    const int64_t want = ceil_div(Qs, kJacHashWarps);
-    const int64_t hgrid = want < (int64_t)sms * hc ? want : (int64_t)sms * hc;
-    k_jaccard_hash<<<(unsigned)hgrid, kJacHashWarps * 32, hsmem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
-                                                                      v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                                      ld_final, H, w.jac_rows, w.jac_count);
-    row_list = w.jac_rows;
+  const char* jac_env = getenv("MPREID_JACCARD");          // "tile": the per-step-barrier kernel (tests / comparison)
+  if (jac_env && jac_env[0] == 't') {
+    // tile: at most 41,600 gallery entries (81 KB) so that two 512-thread CTAs share an SM at MSMT17 size; a gallery
+    // that needs several tiles is covered by several work items per query (each walks the lists once)
+    const int64_t n_tiles = ceil_div(G, kJacMaxTile);
+    int tile_cols = (int)ceil_div(G, n_tiles);
+    tile_cols = (tile_cols + 7) & ~7;
+    const int jac_fixed = (int)((sizeof(JacStage) + 15) & ~size_t(15)) + kJacEntries * 6;
+    const int jac_smem = jac_fixed + tile_cols * 2;
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_fixed + kJacMaxTile * 2 + 16));
+    int ctas_per_sm = (225 * 1024) / (jac_smem + 1024);
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+    const int jac_threads = ctas_per_sm >= 4 ? 256 : 512;
+    const int64_t items = Qs * n_tiles;
+    const int64_t jac_grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
+    k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
+                                                                        v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                        ld_final, tile_cols, (int)n_tiles);
+  } else {
+    // bucket kernel: the whole gallery in one tile when it fits next to the 48 KB entry buffers (up to ~88,000 gallery
+    // samples: one CTA per SM), else equal tiles; small galleries leave room for several CTAs per SM
+    const int fixed = (int)((sizeof(JacBStage) + 15) & ~size_t(15)) + kJacRound * 6;
+    const int max_tile = ((227 * 1024 - 1024 - fixed) / 2) & ~7;
+    const int64_t n_tiles = ceil_div(G, max_tile);
+    int tile_cols = (int)ceil_div(G, n_tiles);
+    tile_cols = (tile_cols + 7) & ~7;
+    const int smem = fixed + tile_cols * 2;
+    MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, fixed + max_tile * 2));
+    int ctas_per_sm = (227 * 1024) / (smem + 1024);
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+    const int64_t items = Qs * n_tiles;
+    const int64_t grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
+    k_jaccard_bucket<<<(unsigned)grid, kJacBWarps * 32, smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
+                                                                    v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                    ld_final, tile_cols, (int)n_tiles);
   }
-  // tile: at most 41,600 gallery entries (81 KB) so that two 512-thread CTAs share an SM at MSMT17 size; a gallery
-  // that needs several tiles is covered by several work items per query (each walks the lists once)
-  const int64_t n_tiles = ceil_div(G, kJacMaxTile);
-  int tile_cols = (int)ceil_div(G, n_tiles);
-  tile_cols = (tile_cols + 7) & ~7;
-  const int jac_fixed = (int)((sizeof(JacStage) + 15) & ~size_t(15)) + kJacEntries * 6;
-  const int jac_smem = jac_fixed + tile_cols * 2;
-  MPREID_CUDA_CHECK(cudaFuncSetAttribute(k_jaccard_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, jac_fixed + kJacMaxTile * 2 + 16));
-  int ctas_per_sm = (225 * 1024) / (jac_smem + 1024);
-  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
-  const int jac_threads = ctas_per_sm >= 4 ? 256 : 512;
-  const int64_t items = Qs * n_tiles;
-  const int64_t jac_grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
-  k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
-                                                                      v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                                      ld_final, tile_cols, (int)n_tiles, row_list, w.jac_count);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }
