@@ -454,8 +454,7 @@ def run_ours(args, data, workload, wkey):
     if args.rerank != "none":
         rq, rg = (Qall, G) if args.rerank == "full" else (min(Qall, 3368), min(G, 15913))
         sub = torch.cat([qf_all[:rq].to(dev) if strong else feats_dev[:rq], feats_dev[Q:Q + rg]])
-        rq_lo, rq_hi = MD.shard_bounds(rq, world, rank)
-        counts = [MD.shard_bounds(rq, world, r)[1] - MD.shard_bounds(rq, world, r)[0] for r in range(world)]
+        rr_rows = [rq]
         rr_q_pid = torch.from_numpy(q_pid_all[:rq]).to(dev)
         rr_q_cam = torch.from_numpy(q_cam_all[:rq]).to(dev)
 
@@ -463,13 +462,14 @@ def run_ours(args, data, workload, wkey):
             p = E.prep_rows(sub, normalize=True, precision=prec, keep_xn=True)   # the fused all-pairs pass reads feature rows
             E.mark("prep")
             if distributed:
-                dfin, _ = MD.rerank_sharded(p, rq, args.k1, args.k2, 0.3, prec)
-            else:
-                dfin = _rerank_device(p, rq, args.k1, args.k2, 0.3, prec)
-            fh, ap, nr = E.rank_eval(dfin, rr_q_pid[rq_lo:rq_hi], lab["g_pid"][:rg], rr_q_cam[rq_lo:rq_hi], lab["g_cam"][:rg], junk)
+                dfin, q_ids = MD.rerank_sharded(p, rq, args.k1, args.k2, 0.3, prec)    # this rank's share of the query rows
+                rr_rows[0] = int(q_ids.numel())
+                fh, ap, nr = E.rank_eval(dfin, rr_q_pid[q_ids], lab["g_pid"][:rg], rr_q_cam[q_ids], lab["g_cam"][:rg], junk)
+                E.mark("rank_eval")
+                return MD.sharded_reduce(fh, ap, nr, None, 50, rg, ids=q_ids, total=rq)   # gathered into global query order
+            dfin = _rerank_device(p, rq, args.k1, args.k2, 0.3, prec)
+            fh, ap, nr = E.rank_eval(dfin, rr_q_pid, lab["g_pid"][:rg], rr_q_cam, lab["g_cam"][:rg], junk)
             E.mark("rank_eval")
-            if distributed:
-                return MD.sharded_reduce(fh, ap, nr, counts, 50, rg)
             return E.reduce_cmc_map(fh.cpu().numpy(), ap.cpu().numpy(), nr.cpu().numpy(), 50, rg)
 
         rr(); torch.cuda.synchronize()
@@ -491,7 +491,7 @@ def run_ours(args, data, workload, wkey):
         Nn = rq + rg
         hbm = pk["hbm"]
         pk3 = pk["bf16_sustained"] / 3.0 if prec in ("3xfp16", "fp32") else peak_tf
-        rows_here = rq_hi - rq_lo
+        rows_here = rr_rows[0]
         st_roof = {}
         if "rerank.all_pairs_gemm" in tl:
             t = tl["rerank.all_pairs_gemm"] * 1e-3

@@ -45,7 +45,8 @@ enum mpreid_metric {
   MPREID_SQEUCLID = 0,      /* ||q||^2+||g||^2-2q.g, no sqrt, no clamp   utils/metrics.py:7-13          */
   MPREID_ARCCOS = 1,        /* arccos(clip(q.g/(|q||g|), +-(1-1e-5)))    utils/metrics.py:15-25         */
   MPREID_ONE_MINUS_DOT = 2, /* 1 - q.g                      processor/processor_uniprompt_stage2.py:466 */
-  MPREID_SQRT_EUCLID = 3    /* sqrt(clamp(sqeuclid, 1e-12))              loss/triplet_loss.py:16-31     */
+  MPREID_SQRT_EUCLID = 3,   /* sqrt(clamp(sqeuclid, 1e-12))              loss/triplet_loss.py:16-31     */
+  MPREID_DOT = 4            /* q.g (similarity logits)                   loss/supcontrast.py:23         */
 };
 
 /* how the q.g contraction is computed */
@@ -132,9 +133,17 @@ MPREID_API int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, cons
 MPREID_API int mpreid_dist_symmetric_topk(const void* xa, const void* xb, const float* x_sqnorm, const float* x_scale,
                                int64_t N, int64_t K, int64_t ldk, int precision,
                                const float* thr, uint64_t* cand, int32_t* cand_cnt, int64_t cand_cap,
-                               int64_t Q, float* out_qg, int64_t ld_out, float* row_max, void* stream);
+                               int64_t Q, float* out_qg, int64_t ld_out, float* row_max, int own_mod, int own_rank, void* stream);
+/* keys (optional, [N, k] uint64): PARTIAL mode for one rank of a multi-GPU run -- the k smallest sort keys
+ * (ordered fp32 bits of value / row_scale, then the column) of what THIS rank's tiles contributed to each row, ~0 = none;
+ * idx / val may then be NULL and only list overflow is reported.  mpreid_merge_topk merges the all-gathered keys_all
+ * [P, N, k] of all ranks into idx / val and validates as above.
+ * own_mod / own_rank of mpreid_dist_symmetric_topk: the launch contracts only the tiles whose 256-row block p satisfies
+ * p % own_mod == own_rank (1 / 0 = all): the row-sharded multi-GPU form; out_qg then holds the rows of those blocks only. */
 MPREID_API int mpreid_cand_topk(const uint64_t* cand, const int32_t* cand_cnt, int64_t cand_cap, int64_t N, int k,
-                     const float* row_scale, const float* thr, int32_t* idx, float* val, int32_t* status, void* stream);
+                     const float* row_scale, const float* thr, int32_t* idx, float* val, uint64_t* keys, int32_t* status, void* stream);
+MPREID_API int mpreid_merge_topk(const uint64_t* keys_all, int P, int64_t N, int k, const float* row_scale, const float* thr,
+                      int32_t* idx, float* val, int32_t* status, void* stream);
 
 /* ---- ranking + CMC / AP ------------------------------------------------------------------------
  * Replaces eval_func (utils/metrics.py:28-88).  The Q x G argsort is never formed: for every query
@@ -209,11 +218,15 @@ MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
 /* General form of mpreid_rerank_finish: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the
  * all-pairs matrix; the pad (Q & 31) for the [Q, G] block mpreid_dist_symmetric_topk keeps; ld_dist >= col0 + N-Q),
  * and the two halves may run as separate calls on the same workspace: stages 1 = query expansion + inverted index
- * (:73-82), 2 = Jaccard + blend (:84-99), 3 = both.                                                             */
+ * (:73-82), 2 = Jaccard + blend (:84-99), 3 = both.
+ * v0_stride: row stride of v0_col / v0_val in entries (0 = mpreid_rerank_v0_capacity; a sharded run all-gathers the V0
+ * rows trimmed to their longest length).  rows_global != 0: dist_q and row_max_q are addressed by the GLOBAL query index
+ * q_ids[il] (the [Q, .] block and the [N] maxima a rank holds in the row-sharded form) instead of the local row il.   */
 MPREID_API int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                             const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                             int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                            float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, void* stream);
+                            float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
+                            int64_t v0_stride, int rows_global, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);
@@ -225,6 +238,30 @@ MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* ro
  * other-label entries gets dist_an = +inf, n_inds = -1.                                              */
 MPREID_API int mpreid_hard_example_mining(const float* dist, int64_t ld_dist, int64_t N, const int64_t* labels,
                                float* dist_ap, float* dist_an, int64_t* p_inds, int64_t* n_inds, void* stream);
+
+/* ---- batch-hard triplet distances with a backward (loss/triplet_loss.py:16-31,50-103) ------------------
+ * forward: x [B, D] fp32 -> the pairwise sqrt/clamp euclidean distances of the batch against itself, mined in the same
+ * kernel: dist_ap[i] = max over same-label j (diagonal included), dist_an[i] = min over other-label j (+inf, n_inds = -1
+ * if there is none), p_inds / n_inds = the selected columns (lowest index on ties).
+ * backward: grad_x [B, D] = d(sum_i g_ap[i] dist_ap[i] + g_an[i] dist_an[i]) / dx, zero through an active clamp;
+ * gathered per row in a fixed order (no atomics: bit-reproducible).                                                */
+MPREID_API int mpreid_triplet_forward(const float* x, int64_t ld_x, int64_t B, int64_t D, const int64_t* labels,
+                           float* dist_ap, float* dist_an, int64_t* p_inds, int64_t* n_inds, void* stream);
+MPREID_API int mpreid_triplet_backward(const float* x, int64_t ld_x, int64_t B, int64_t D, const int64_t* p_inds, const int64_t* n_inds,
+                            const float* dist_ap, const float* dist_an, const float* g_ap, const float* g_an,
+                            float* grad_x, int64_t ld_g, void* stream);
+
+/* ---- stage-1 contrastive step on cached features (loss/supcontrast.py:17-31, called twice by
+ * processor/processor_uniprompt_stage1.py:88-93) ----------------------------------------------------
+ * S [Ba, Bb] = A.B^T (mpreid_dist_matrix with MPREID_DOT).  loss[0] = SupConLoss(A, B, labels_a, labels_b) (rows of S),
+ * and with both_directions: loss[1] = SupConLoss(B, A, ...) (columns of S), loss[2] = their sum.  grad_a / grad_b
+ * (optional, [Ba, D] / [Bb, D]) = d(grad_scale_rows * loss[0] + grad_scale_cols * loss[1]) / dA, dB.                */
+MPREID_API size_t mpreid_supcon_workspace_bytes(int64_t Ba, int64_t Bb);
+MPREID_API int mpreid_supcon_step(const float* S, int64_t ld_s, int64_t Ba, int64_t Bb, const int64_t* labels_a, const int64_t* labels_b,
+                       float temperature, int both_directions, float grad_scale_rows, float grad_scale_cols,
+                       const float* a, int64_t ld_a, const float* b, int64_t ld_b, int64_t D,
+                       float* loss, float* grad_a, int64_t ld_ga, float* grad_b, int64_t ld_gb,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-side hooks (no GPU needed) -----------------------------------------------------------
  * The scalar arithmetic the kernels run is __host__ __device__ code; these two entry points run it

@@ -15,12 +15,12 @@ LIB_PATH = os.path.join(HERE, "libmpreid_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mpreid_b200.h")
 
 # enums of include/mpreid_b200.h
-SQEUCLID, ARCCOS, ONE_MINUS_DOT, SQRT_EUCLID = 0, 1, 2, 3
+SQEUCLID, ARCCOS, ONE_MINUS_DOT, SQRT_EUCLID, DOT = 0, 1, 2, 3, 4
 FP32_SIMT, X3TF32, BF16, X3FP16, X2FP16 = 0, 1, 2, 3, 4
 JUNK_NONE, JUNK_PID_CAM = 0, 1
 
 METRICS = {"sqeuclid": SQEUCLID, "euclidean": SQEUCLID, "arccos": ARCCOS, "cosine": ARCCOS,
-           "one_minus_dot": ONE_MINUS_DOT, "1-cos": ONE_MINUS_DOT, "sqrt_euclid": SQRT_EUCLID}
+           "one_minus_dot": ONE_MINUS_DOT, "1-cos": ONE_MINUS_DOT, "sqrt_euclid": SQRT_EUCLID, "dot": DOT}
 PRECISIONS = {"simt": FP32_SIMT, "fp32_simt": FP32_SIMT, "3xtf32": X3TF32, "bf16": BF16, "3xfp16": X3FP16, "fp32": X3FP16, "2xfp16": X2FP16}
 JUNKS = {"none": JUNK_NONE, "pid_cam": JUNK_PID_CAM}
 
@@ -44,11 +44,16 @@ SIGNATURES = {
     "mpreid_rerank_build_v0": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p]),
     "mpreid_rerank_finish_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mpreid_rerank_finish": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p]),
-    "mpreid_dist_symmetric_topk": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
-    "mpreid_cand_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "mpreid_dist_symmetric_topk": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i32, _i32, _p]),
+    "mpreid_cand_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "mpreid_merge_topk": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "mpreid_rerank_build_v0_sparse": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
-    "mpreid_rerank_finish_ex": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _i32, _p]),
+    "mpreid_rerank_finish_ex": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _i32, _i64, _i32, _p]),
     "mpreid_hard_example_mining": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "mpreid_triplet_forward": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "mpreid_triplet_backward": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "mpreid_supcon_workspace_bytes": (_sz, [_i64, _i64]),
+    "mpreid_supcon_step": (_i32, [_p, _i64, _i64, _i64, _p, _p, _f32, _i32, _f32, _f32, _p, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _sz, _p]),
     "mpreid_host_average_precision": (C.c_double, [_p, _i32, _i64]),
     "mpreid_host_order_keys": (None, [_p, _i64, _p]),
 }

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpreid_b200.so")
-SOURCES = ["api.cu", "prep.cu", "dist_simt.cu", "dist_tc.cu", "rank_eval.cu", "topk.cu", "rerank.cu", "mining.cu"]
+SOURCES = ["api.cu", "prep.cu", "dist_simt.cu", "dist_tc.cu", "rank_eval.cu", "topk.cu", "rerank.cu", "mining.cu", "triplet.cu", "supcon.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

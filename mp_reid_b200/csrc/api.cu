@@ -59,8 +59,8 @@ extern "C" int mpreid_dist_matrix(const void* qa, const void* qb, const void* ga
   MPREID_REQUIRE(Q > 0 && G > 0 && K > 0 && ldk >= K && ld_out >= G && Q < INT32_MAX && G < INT32_MAX,
                  "dist_matrix: bad shape Q=%lld G=%lld K=%lld ldk=%lld ld_out=%lld", (long long)Q, (long long)G,
                  (long long)K, (long long)ldk, (long long)ld_out);
-  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_SQRT_EUCLID, "dist_matrix: unknown metric %d", metric);
-  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || (q_aux && g_aux), "dist_matrix: metric %d needs q_aux/g_aux", metric);
+  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_DOT, "dist_matrix: unknown metric %d", metric);
+  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || metric == MPREID_DOT || (q_aux && g_aux), "dist_matrix: metric %d needs q_aux/g_aux", metric);
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MPREID_FP32_SIMT)
     return launch_dist_simt((const float*)qa, (const float*)ga, q_aux, g_aux, Q, G, K, ldk, metric, out, ld_out, row_max, st);
@@ -78,8 +78,8 @@ extern "C" int mpreid_dist_matrix_symmetric(const void* xa, const void* xb, cons
   MPREID_REQUIRE(xa && out, "dist_matrix_symmetric: null operand");
   MPREID_REQUIRE(N > 0 && K > 0 && ldk >= K && ld_out >= N && N < INT32_MAX, "dist_matrix_symmetric: bad shape N=%lld K=%lld", (long long)N,
                  (long long)K);
-  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_SQRT_EUCLID, "dist_matrix_symmetric: unknown metric %d", metric);
-  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || x_aux, "dist_matrix_symmetric: metric %d needs x_aux", metric);
+  MPREID_REQUIRE(metric >= MPREID_SQEUCLID && metric <= MPREID_DOT, "dist_matrix_symmetric: unknown metric %d", metric);
+  MPREID_REQUIRE(metric == MPREID_ONE_MINUS_DOT || metric == MPREID_DOT || x_aux, "dist_matrix_symmetric: metric %d needs x_aux", metric);
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == MPREID_FP32_SIMT)   // the validation kernel has no mirrored mode: plain all-pairs launch
     return launch_dist_simt((const float*)xa, (const float*)xa, x_aux, x_aux, N, N, K, ldk, metric, out, ld_out, row_max, st);
@@ -104,8 +104,9 @@ extern "C" void mpreid_host_order_keys(const float* values_host, int64_t n, uint
 extern "C" int mpreid_dist_symmetric_topk(const void* xa, const void* xb, const float* x_sqnorm, const float* x_scale,
                                           int64_t N, int64_t K, int64_t ldk, int precision,
                                           const float* thr, uint64_t* cand, int32_t* cand_cnt, int64_t cand_cap,
-                                          int64_t Q, float* out_qg, int64_t ld_out, float* row_max, void* stream) {
+                                          int64_t Q, float* out_qg, int64_t ld_out, float* row_max, int own_mod, int own_rank, void* stream) {
   MPREID_REQUIRE(xa && x_sqnorm && thr && cand && cand_cnt && out_qg && row_max, "dist_symmetric_topk: null pointer");
+  MPREID_REQUIRE(own_mod >= 1 && own_rank >= 0 && own_rank < own_mod, "dist_symmetric_topk: bad tile ownership %d of %d", own_rank, own_mod);
   MPREID_REQUIRE(N > 1 && K > 0 && ldk >= K && N < INT32_MAX && Q > 0 && Q < N, "dist_symmetric_topk: bad shape N=%lld Q=%lld", (long long)N, (long long)Q);
   MPREID_REQUIRE(cand_cap >= 1 && cand_cap < (1 << 24) && ld_out >= (N - Q) + (Q & 31), "dist_symmetric_topk: bad candidate capacity / ld_out");
   MPREID_REQUIRE(precision == MPREID_3XTF32 || precision == MPREID_BF16 || precision == MPREID_3XFP16 || precision == MPREID_2XFP16,
@@ -115,6 +116,7 @@ extern "C" int mpreid_dist_symmetric_topk(const void* xa, const void* xb, const 
   TopkFuse f;
   f.thr = thr; f.cand = (unsigned long long*)cand; f.cand_cnt = cand_cnt; f.cap = (int)cand_cap;
   f.keep_rows = (int)Q; f.keep_col0 = (int)(Q & ~(int64_t)31);
+  f.own_mod = own_mod; f.own_rank = own_rank;
   return launch_dist_tc(xa, xb, xa, xb, x_sqnorm, x_sqnorm, x_scale, x_scale, N, N, ldk, MPREID_SQEUCLID, precision, out_qg, ld_out, row_max, 1,
                         (cudaStream_t)stream, &f);
 }

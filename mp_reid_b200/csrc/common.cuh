@@ -153,6 +153,7 @@ struct TopkFuse {
   int cap;
   int keep_rows;                 // Q: rows < Q ...
   int keep_col0;                 // ... and columns >= keep_col0 (= Q rounded down to 32) are stored at out[row, col - keep_col0]
+  int own_mod, own_rank;         // multi-GPU: this launch contracts only the tiles of the 256-row blocks p with p % own_mod == own_rank
 };
 
 // np.around(k1 / 2) -- round half to even (utils/reranking.py:60)

@@ -397,6 +397,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         // symmetric mode: tiles below the diagonal block column are never visited, the mirrors fill them
         const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric, band);
+        if (FUSE && fuse.own_mod > 1 && ((t.m_blk >> 1) % fuse.own_mod) != fuse.own_rank) continue;   // another rank's row block
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -427,6 +428,10 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {
+      if (FUSE && fuse.own_mod > 1) {
+        const TileCoord t = tile_coord<CTA2>(tile, 0, m_blocks, n_blocks, symmetric, band);
+        if (((t.m_blk >> 1) % fuse.own_mod) != fuse.own_rank) continue;
+      }
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       ++it;
@@ -546,6 +551,7 @@ k_dist_tc(const __grid_constant__ Maps maps, const float* __restrict__ q_aux, co
     int it = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const TileCoord t = tile_coord<CTA2>(tile, (int)cta_rank, m_blocks, n_blocks, symmetric, band);
+      if (FUSE && fuse.own_mod > 1 && ((t.m_blk >> 1) % fuse.own_mod) != fuse.own_rank) continue;
       // symmetric (all-pairs) mode: a tile strictly right of the diagonal block column also writes its
       // transpose, which is exactly the set of tiles skipped above; diagonal tiles (n == m/2) do not
       const bool mirror = symmetric && t.n_blk > (t.m_blk >> 1);
@@ -765,6 +771,7 @@ static int launch(const void* qa, const void* qb, const void* ga, const void* gb
     case MPREID_SQEUCLID: MPREID_PICK(MPREID_SQEUCLID); break;
     case MPREID_ARCCOS: MPREID_PICK(MPREID_ARCCOS); break;
     case MPREID_ONE_MINUS_DOT: MPREID_PICK(MPREID_ONE_MINUS_DOT); break;
+    case MPREID_DOT: MPREID_PICK(MPREID_DOT); break;
     default: MPREID_PICK(MPREID_SQRT_EUCLID); break;
   }
 #undef MPREID_PICK

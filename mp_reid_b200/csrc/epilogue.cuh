@@ -17,6 +17,8 @@ __device__ __forceinline__ float finish_distance(float dot, float qa, float ga) 
     return acosf(c);
   } else if (METRIC == MPREID_ONE_MINUS_DOT) {
     return 1.0f - dot;  // processor/processor_uniprompt_stage2.py:466-467
+  } else if (METRIC == MPREID_DOT) {
+    return dot;         // loss/supcontrast.py:23 (text @ image^T)
   } else {
     // loss/triplet_loss.py:26-30
     return sqrtf(fmaxf(fmaf(-2.0f, dot, qa + ga), 1e-12f));
@@ -28,6 +30,7 @@ __device__ __forceinline__ float finish_distance_rt(int metric, float dot, float
     case MPREID_SQEUCLID: return finish_distance<MPREID_SQEUCLID>(dot, qa, ga);
     case MPREID_ARCCOS: return finish_distance<MPREID_ARCCOS>(dot, qa, ga);
     case MPREID_ONE_MINUS_DOT: return finish_distance<MPREID_ONE_MINUS_DOT>(dot, qa, ga);
+    case MPREID_DOT: return finish_distance<MPREID_DOT>(dot, qa, ga);
     default: return finish_distance<MPREID_SQRT_EUCLID>(dot, qa, ga);
   }
 }

@@ -537,7 +537,7 @@ __device__ __forceinline__ float jaccard_blend(float a /*temp_min != 0*/, float 
 template <bool VEC>
 __global__ void __launch_bounds__(kBlendThreads)
 k_blend_default(const float* __restrict__ dist, int64_t ld, int64_t col0, int Qs, int G, float lambda_value,
-                const float* __restrict__ rowmax, float* __restrict__ final_dist, int64_t ld_final) {
+                const float* __restrict__ rowmax, float* __restrict__ final_dist, int64_t ld_final, const int32_t* __restrict__ src_rows) {
   const float base = __half2float(__float2half_rn((float)(1.0 - (double)lambda_value)));
   constexpr int kChunk = kBlendThreads * kBlendPer;
   const int chunks = (G + kChunk - 1) / kChunk;
@@ -545,8 +545,9 @@ k_blend_default(const float* __restrict__ dist, int64_t ld, int64_t col0, int Qs
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int il = (int)(w / chunks);
     const int c0 = (int)(w - (int64_t)il * chunks) * kChunk;
-    const float rmax = __ldg(rowmax + il);
-    const float* drow = dist + (int64_t)il * ld + col0;
+    const int sr = src_rows ? src_rows[il] : il;   // row of `dist` / `rowmax` that holds query il (its global index in the sharded form)
+    const float rmax = __ldg(rowmax + sr);
+    const float* drow = dist + (int64_t)sr * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
     if (VEC) {
       // both rows 16-byte aligned: two float4 per thread, 512 B per warp instruction
@@ -611,7 +612,7 @@ k_jaccard_bucket(const float* __restrict__ dist, int64_t ld, int64_t col0, const
                  float lambda_value, const float* __restrict__ rowmax,
                  const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
                  const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles) {
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles, int rows_global) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacBStage& st = *reinterpret_cast<JacBStage*>(smem_raw);
   int32_t* ent_c = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(JacBStage) + 15) & ~size_t(15)));   // [kJacRound] column inside the tile
@@ -665,16 +666,34 @@ k_jaccard_bucket(const float* __restrict__ dist, int64_t ld, int64_t col0, const
         __syncwarp();
         int step = 0;
 #pragma unroll
-        for (int it = 0; it < kJacPerLane; ++it) {
-          const int x = w0 + it * 32 + lane;
-          ec[it] = -1; em[it] = 0; eo[it] = -1;
-          if (x < w1) {
-            const int xf = r0 + x;
-            while (st.pre[step + 1] <= xf) ++step;             // monotone in it: amortised O(1)
-            const int64_t src = st.b[step] + (xf - st.pre[step]);
-            const unsigned c = (unsigned)(csc_row[src] - gbase);
-            if (c < (unsigned)tn) {
-              const __half vg = __ushort_as_half(csc_val[src]), vik = __ushort_as_half(st.v[step]);
+        for (int h = 0; h < kJacPerLane / 8; ++h) {
+          // addresses first, then all sixteen loads of the half in flight, then the arithmetic: a load whose value is
+          // consumed right away would cost one full memory latency per entry
+          int64_t src[8]; uint16_t vk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int x = w0 + (h * 8 + u) * 32 + lane;
+            src[u] = -1; vk[u] = 0;
+            if (x < w1) {
+              const int xf = r0 + x;
+              while (st.pre[step + 1] <= xf) ++step;             // monotone in x: amortised O(1)
+              src[u] = st.b[step] + (xf - st.pre[step]);
+              vk[u] = st.v[step];
+            }
+          }
+          int32_t gg[8]; uint16_t ww[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            gg[u] = 0; ww[u] = 0;
+            if (src[u] >= 0) { gg[u] = __ldg(csc_row + src[u]); ww[u] = __ldg(csc_val + src[u]); }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = h * 8 + u;
+            ec[it] = -1; em[it] = 0; eo[it] = -1;
+            const unsigned c = (unsigned)(gg[u] - gbase);
+            if (src[u] >= 0 && c < (unsigned)tn) {
+              const __half vg = __ushort_as_half(ww[u]), vik = __ushort_as_half(vk[u]);
               em[it] = __half_as_ushort(__hlt(vg, vik) ? vg : vik);                        // np.minimum on fp16  (:90-91)
               ec[it] = (int32_t)c;
               eo[it] = (int8_t)min(kJacBWarps - 1, (int)((float)c * own_scale));
@@ -737,26 +756,53 @@ k_jaccard_bucket(const float* __restrict__ dist, int64_t ld, int64_t col0, const
       }
     }
     __syncthreads();       // (also covers len == 0: the zero fill is complete)
-    // touched entries only: Jaccard + blend, overwriting the default
-    const float rmax = rowmax[il];
-    const float* drow = dist + (int64_t)il * ld + col0;
+    // touched entries only: Jaccard + blend, overwriting the default.  The tile is swept in slices; the touched entries
+    // of a slice are first collected in the entry buffers, then blended with four independent distance loads per thread
+    // in flight (the reads are scattered: one dependent load per entry would serialise the memory latency)
+    const int sr = rows_global ? i : il;   // sharded form: distance rows and maxima are addressed by the global query index
+    const float rmax = rowmax[sr];
+    const float* drow = dist + (int64_t)sr * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
-    for (int c8 = tid; c8 < n8; c8 += kJacBWarps * 32) {
-      const uint4 w = a4[c8];
-      if ((w.x | w.y | w.z | w.w) == 0u) continue;
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    int* fix_n = &st.cnt[0][0];
+    constexpr int kSlice8 = kJacRound / 8;                       // uint4 chunks per slice: at most kJacRound entries
+    for (int s8 = 0; s8 < n8; s8 += kSlice8) {
+      if (tid == 0) *fix_n = 0;
+      __syncthreads();
+      const int e8 = min(n8, s8 + kSlice8);
+      for (int c8 = s8 + tid; c8 < e8; c8 += kJacBWarps * 32) {
+        const uint4 w = a4[c8];
+        if ((w.x | w.y | w.z | w.w) == 0u) continue;
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
-        const int c = c8 * 8 + j;
-        if ((hb & 0x7fffu) != 0 && c < tn) {
-          const float a = __half2float(__ushort_as_half(hb));
-          const float dn = drow[t0 + c] / rmax;                                          // original_dist[i, Q+g]   (:46,72)
-          orow[t0 + c] = jaccard_blend(a, dn, lambda_value, one_minus_lambda);
+        for (int j = 0; j < 8; ++j) {
+          const uint16_t hb = (uint16_t)(ww[j >> 1] >> ((j & 1) * 16));
+          const int c = c8 * 8 + j;
+          if ((hb & 0x7fffu) != 0 && c < tn) {
+            const int pos = atomicAdd(fix_n, 1);
+            ent_c[pos] = c; ent_m[pos] = hb;
+          }
         }
       }
+      __syncthreads();
+      const int nf = *fix_n;
+      for (int x0 = tid; x0 < nf; x0 += 4 * kJacBWarps * 32) {
+        float dv[4]; int cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int x = x0 + u * kJacBWarps * 32;
+          cc[u] = x < nf ? ent_c[x] : -1;
+          dv[u] = cc[u] >= 0 ? __ldg(drow + t0 + cc[u]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (cc[u] >= 0) {
+            const float a = __half2float(__ushort_as_half(ent_m[x0 + u * kJacBWarps * 32]));
+            orow[t0 + cc[u]] = jaccard_blend(a, dv[u] / rmax, lambda_value, one_minus_lambda);   // original_dist[i, Q+g] (:46,72)
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();       // the tile is zeroed again by the next item
   }
 }
 
@@ -791,7 +837,7 @@ k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const
                  float lambda_value, const float* __restrict__ rowmax,
                  const int32_t* __restrict__ v_col, const uint16_t* __restrict__ v_val, const int32_t* __restrict__ v_len, int64_t C1,
                  const int64_t* __restrict__ col_off, const int32_t* __restrict__ csc_row, const uint16_t* __restrict__ csc_val,
-                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles) {
+                 float* __restrict__ final_dist, int64_t ld_final, int tile_cols, int n_tiles, int rows_global) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   JacStage& st = *reinterpret_cast<JacStage*>(smem_raw);
   int32_t* ent_g = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(JacStage) + 15) & ~size_t(15)));   // [kJacEntries]
@@ -885,8 +931,9 @@ k_jaccard_sparse(const float* __restrict__ dist, int64_t ld, int64_t col0, const
     }
     __syncthreads();       // (also covers len == 0: the zero fill is complete)
     // touched entries only: Jaccard + blend, overwriting the default
-    const float rmax = rowmax[il];
-    const float* drow = dist + (int64_t)il * ld + col0;
+    const int sr = rows_global ? i : il;
+    const float rmax = rowmax[sr];
+    const float* drow = dist + (int64_t)sr * ld + col0;
     float* orow = final_dist + (int64_t)il * ld_final;
     for (int c8 = tid; c8 < n8; c8 += T) {
       const uint4 w = a4[c8];
@@ -1005,9 +1052,11 @@ namespace mpreid {
 static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                               const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                               int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                              float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, cudaStream_t st) {
+                              float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, int64_t v0_stride,
+                              int rows_global, cudaStream_t st) {
   MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_q && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
   MPREID_REQUIRE(stages >= 1 && stages <= 3, "rerank_finish: stages must be 1 (expand + index), 2 (Jaccard + blend) or 3 (both)");
+  MPREID_REQUIRE(!rows_global || q_ids, "rerank_finish: rows_global needs q_ids");
   MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= col0 + (N - Q) && ld_final >= N - Q,
                  "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
   MPREID_REQUIRE(k1 >= 1 && k1 <= kMaxK1 && k2 >= 1 && k2 <= 64 && K >= neighbor_count(k1, k2), "rerank_finish: bad k1/k2/K");
@@ -1029,10 +1078,11 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
       // rows whose k2 gathered V0 rows hold <= 512 entries: one warp each; the rest (large k1 / k2): one CTA each
       const int k2e = k2 < Keff ? k2 : Keff;
       const int64_t wgrid = ceil_div(N, kQeWarps) < (int64_t)sms * 6 ? ceil_div(N, kQeWarps) : (int64_t)sms * 6;
-      k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, w.C0,
+      const int v0s = (int)(v0_stride > 0 ? v0_stride : w.C0);   // row stride of the V0 arrays (the capacity, or a trimmed width)
+      k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
                                                                    w.v_col, w.v_val, w.v_len, w.C1);
       const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
-      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, w.C0,
+      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
                                                                w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P, kQeWarpEntries);
     }
     // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
@@ -1051,8 +1101,9 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     const bool vec = (((uintptr_t)(dist_q + col0) | (uintptr_t)final_dist) & 15) == 0 && ld_dist % 4 == 0 && ld_final % 4 == 0;
     const int64_t work = Qs * ceil_div(G, kBlendThreads * kBlendPer);
     const int64_t grid = work < (int64_t)sms * 16 ? work : (int64_t)sms * 16;
-    if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
-    else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final);
+    const int32_t* src_rows = rows_global ? q_ids : nullptr;
+    if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
+    else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
   }
   const char* jac_env = getenv("MPREID_JACCARD");          // "tile": the per-step-barrier kernel (tests / comparison)
   if (jac_env && jac_env[0] == 't') {
@@ -1071,7 +1122,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     const int64_t jac_grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
     k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
                                                                         v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                                        ld_final, tile_cols, (int)n_tiles);
+                                                                        ld_final, tile_cols, (int)n_tiles, rows_global);
   } else {
     // bucket kernel: the whole gallery in one tile when it fits next to the 48 KB entry buffers (up to ~88,000 gallery
     // samples: one CTA per SM), else equal tiles; small galleries leave room for several CTAs per SM
@@ -1088,7 +1139,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     const int64_t grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
     k_jaccard_bucket<<<(unsigned)grid, kJacBWarps * 32, smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
                                                                     v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
-                                                                    ld_final, tile_cols, (int)n_tiles);
+                                                                    ld_final, tile_cols, (int)n_tiles, rows_global);
   }
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
@@ -1101,7 +1152,7 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                                     int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                                     float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qrows, ld_dist, Q, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, 3, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, 3, 0, 0, (cudaStream_t)stream);
 }
 
 // General form: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the all-pairs matrix, 0 or the
@@ -1110,10 +1161,11 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
 extern "C" int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                                        const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                                        int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
-                                       float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, void* stream) {
-  MPREID_REQUIRE(col0 >= 0, "rerank_finish_ex: col0 < 0");
+                                       float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
+                                       int64_t v0_stride, int rows_global, void* stream) {
+  MPREID_REQUIRE(col0 >= 0 && v0_stride >= 0, "rerank_finish_ex: col0 / v0_stride < 0");
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_q, ld_dist, col0, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, stages, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, stages, v0_stride, rows_global, (cudaStream_t)stream);
 }
 
 // single-GPU convenience: neighbours + V0 rows + finish on the whole matrix

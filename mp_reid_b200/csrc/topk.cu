@@ -285,7 +285,7 @@ k_row_topk(const float* __restrict__ dist, int64_t ld, int Q, int G, int k, cons
 __global__ void __launch_bounds__(kTopkThreads)
 k_cand_topk(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int64_t cand_cap, int N, int k,
             const float* __restrict__ row_scale, const float* __restrict__ thr,
-            int32_t* __restrict__ idx_out, float* __restrict__ val_out, int32_t* status, int cap) {
+            int32_t* __restrict__ idx_out, float* __restrict__ val_out, unsigned long long* __restrict__ keys_out, int32_t* status, int cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
@@ -296,6 +296,7 @@ k_cand_topk(const unsigned long long* __restrict__ cand, const int* __restrict__
   const int keff = min(k, N);
   const int drain_at = cap - kTopkChunk;
   const bool has_scale = row_scale != nullptr;
+  const bool partial = keys_out != nullptr;   // one rank's share of the row: fewer than k entries is normal, the merge validates
   for (int row_i = blockIdx.x * warps + warp; row_i < N; row_i += gridDim.x * warps) {
     const float r = has_scale ? row_scale[row_i] : 1.0f;
     const int cnt_all = cand_cnt[row_i];
@@ -315,13 +316,18 @@ k_cand_topk(const unsigned long long* __restrict__ cand, const int* __restrict__
     for (int i = st.count + lane; i < P; i += 32) w.q[i] = ~0ull;
     __syncwarp();
     warp_bitonic(w, P);
-    bool bad = cnt_all > cand_cap || st.count < keff;
-    if (!bad && keff > 0) {
+    bool bad = cnt_all > cand_cap || (!partial && st.count < keff);
+    if (!bad && !partial && keff > 0) {
       const float t = has_scale ? thr[row_i] / r : thr[row_i];
       bad = !((uint32_t)(w.q[keff - 1] >> 32) < order_key(t));
     }
     if (bad && lane == 0) atomicAdd(&status[0], 1);
     if (lane == 0) atomicMax(&status[1], cnt_all);
+    if (partial) {
+      for (int i = lane; i < k; i += 32) keys_out[(int64_t)row_i * k + i] = (i < keff && i < st.count) ? w.q[i] : ~0ull;
+      __syncwarp();
+      continue;
+    }
     for (int i = lane; i < k; i += 32) {
       int32_t id = -1;
       float val = INFINITY;
@@ -331,6 +337,46 @@ k_cand_topk(const unsigned long long* __restrict__ cand, const int* __restrict__
       }
       idx_out[(int64_t)row_i * k + i] = id;
       if (val_out) val_out[(int64_t)row_i * k + i] = val;
+    }
+    __syncwarp();
+  }
+}
+
+// Merge of per-rank partial selections (row-sharded multi-GPU re-ranking): keys_all [P, N, k] holds, per rank, the k smallest
+// sort keys of the row among the tiles that rank contracted (~0 = none).  The union contains the k smallest of the whole
+// row; one warp per row sorts the P * k keys and validates like k_cand_topk (k valid keys, k-th strictly below thr).
+static constexpr int kMergeMax = 1024;
+__global__ void __launch_bounds__(128)
+k_merge_topk(const unsigned long long* __restrict__ keys_all, int P, int N, int k, const float* __restrict__ row_scale,
+             const float* __restrict__ thr, int32_t* __restrict__ idx_out, float* __restrict__ val_out, int32_t* status) {
+  __shared__ uint64_t sbuf[4][kMergeMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSel w;
+  w.q = sbuf[warp]; w.hist = nullptr; w.lane = lane;
+  const int keff = min(k, N);
+  const int T = P * k;
+  const int Pw = (int)next_pow2_u32((uint32_t)T);
+  for (int row_i = blockIdx.x * 4 + warp; row_i < N; row_i += gridDim.x * 4) {
+    for (int t = lane; t < Pw; t += 32) {
+      uint64_t key = ~0ull;
+      if (t < T) { const int p = t / k, e = t - p * k; key = keys_all[((int64_t)p * N + row_i) * k + e]; }
+      w.q[t] = key;
+    }
+    __syncwarp();
+    warp_bitonic(w, Pw);
+    const float r = row_scale ? row_scale[row_i] : 1.0f;
+    bool bad = false;
+    if (keff > 0) {
+      const uint64_t kth = w.q[keff - 1];
+      const float t = row_scale ? thr[row_i] / r : thr[row_i];
+      bad = kth == ~0ull || !((uint32_t)(kth >> 32) < order_key(t));
+    }
+    if (bad && lane == 0) atomicAdd(&status[0], 1);
+    for (int i = lane; i < k; i += 32) {
+      int32_t id = -1; float val = INFINITY;
+      if (i < keff && w.q[i] != ~0ull) { id = (int32_t)(w.q[i] & 0xffffffffu); val = order_key_inv((uint32_t)(w.q[i] >> 32)); }
+      idx_out[(int64_t)row_i * k + i] = id;
+      val_out[(int64_t)row_i * k + i] = val;
     }
     __syncwarp();
   }
@@ -401,8 +447,8 @@ extern "C" int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int
 }
 
 extern "C" int mpreid_cand_topk(const uint64_t* cand, const int32_t* cand_cnt, int64_t cand_cap, int64_t N, int k,
-                                const float* row_scale, const float* thr, int32_t* idx, float* val, int32_t* status, void* stream) {
-  MPREID_REQUIRE(cand && cand_cnt && thr && idx && status && N > 0 && N < INT32_MAX && cand_cap >= 1, "cand_topk: bad arguments");
+                                const float* row_scale, const float* thr, int32_t* idx, float* val, uint64_t* keys, int32_t* status, void* stream) {
+  MPREID_REQUIRE(cand && cand_cnt && thr && (idx || keys) && status && N > 0 && N < INT32_MAX && cand_cap >= 1, "cand_topk: bad arguments");
   MPREID_REQUIRE(k >= 1 && k <= kTopkMaxK, "cand_topk: k must be in [1, %d], got %d", kTopkMaxK, k);
   int cap = (2 * k > 256 ? 2 * k : 256) + kTopkChunk;
   cap = (cap + 31) / 32 * 32;
@@ -419,7 +465,20 @@ extern "C" int mpreid_cand_topk(const uint64_t* cand, const int32_t* cand_cnt, i
   const int64_t want = ceil_div(N, warps);
   const int64_t grid = want < (int64_t)sms * ctas_per_sm ? want : (int64_t)sms * ctas_per_sm;
   k_cand_topk<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>((const unsigned long long*)cand, cand_cnt, cand_cap, (int)N, k, row_scale, thr,
-                                                                          idx, val, status, cap);
+                                                                          idx, val, (unsigned long long*)keys, status, cap);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+extern "C" int mpreid_merge_topk(const uint64_t* keys_all, int P, int64_t N, int k, const float* row_scale, const float* thr,
+                                 int32_t* idx, float* val, int32_t* status, void* stream) {
+  MPREID_REQUIRE(keys_all && thr && idx && val && status && P >= 1 && N > 0 && N < INT32_MAX && k >= 1, "merge_topk: bad arguments");
+  MPREID_REQUIRE((int64_t)P * k <= kMergeMax, "merge_topk: ranks * k = %lld exceeds %d", (long long)P * k, kMergeMax);
+  MPREID_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));
+  const int sms = sm_count_of_current_device();
+  const int64_t want = ceil_div(N, 4);
+  const int64_t grid = want < (int64_t)sms * 6 ? want : (int64_t)sms * 6;
+  k_merge_topk<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const unsigned long long*)keys_all, P, (int)N, k, row_scale, thr, idx, val, status);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

@@ -77,31 +77,50 @@ def broadcast_gallery(gf: torch.Tensor | None, g_pid, g_cam, shape=None, src: in
     return gf, g_pid, g_cam
 
 
-def gather_per_query(first_hit: torch.Tensor, ap: torch.Tensor, num_rel: torch.Tensor, counts: list[int], group=None):
+def gather_per_query(first_hit: torch.Tensor, ap: torch.Tensor, num_rel: torch.Tensor, counts: list[int] | None, group=None,
+                     ids: torch.Tensor | None = None, total: int | None = None):
     """All-gather the per-query results of every rank (one collective) -> numpy arrays in global query order.
 
-    counts[r] = number of queries of rank r (shards may be ragged); the payload is padded to max(counts).
+    counts[r] = number of queries of rank r when the shards are contiguous (shards may be ragged; the payload is padded
+    to max(counts)).  ids (with total = number of queries overall): the GLOBAL query index of every local result instead,
+    for shards that are not contiguous (block-cyclic re-ranking); results are scattered into place by it.
     first_hit / num_rel travel as float64 (exact for |x| < 2^53) next to the float64 AP.
     """
     world = dist.get_world_size(group)
-    width = max(counts)
-    packed = torch.zeros((3, width), dtype=torch.float64, device=ap.device)
     n = ap.shape[0]
+    if ids is None:
+        width, rows = max(counts), 3
+    else:
+        width, rows = (total + world - 1) // world + 512, 4     # an upper bound every rank can compute (256-row blocks, cyclic)
+    packed = torch.zeros((rows, width), dtype=torch.float64, device=ap.device)
     packed[0, :n] = first_hit.to(torch.float64)
     packed[1, :n] = ap
     packed[2, :n] = num_rel.to(torch.float64)
-    out = torch.empty((world * 3, width), dtype=torch.float64, device=ap.device)  # concatenation along dim 0
+    if ids is not None:
+        packed[3].fill_(-1.0)
+        packed[3, :n] = ids.to(torch.float64)
+    out = torch.empty((world * rows, width), dtype=torch.float64, device=ap.device)  # concatenation along dim 0
     all_gather_into(out, packed, group)
-    h = out.cpu().numpy().reshape(world, 3, width)
-    fh = np.concatenate([h[r, 0, :counts[r]] for r in range(world)]).astype(np.int32)
-    apv = np.concatenate([h[r, 1, :counts[r]] for r in range(world)])
-    nr = np.concatenate([h[r, 2, :counts[r]] for r in range(world)]).astype(np.int32)
+    h = out.cpu().numpy().reshape(world, rows, width)
+    if ids is None:
+        fh = np.concatenate([h[r, 0, :counts[r]] for r in range(world)]).astype(np.int32)
+        apv = np.concatenate([h[r, 1, :counts[r]] for r in range(world)])
+        nr = np.concatenate([h[r, 2, :counts[r]] for r in range(world)]).astype(np.int32)
+        return fh, apv, nr
+    fh, apv, nr = np.zeros(total, np.int32), np.zeros(total, np.float64), np.zeros(total, np.int32)
+    seen = 0
+    for r in range(world):
+        keep = h[r, 3] >= 0
+        at = h[r, 3][keep].astype(np.int64)
+        fh[at], apv[at], nr[at] = h[r, 0][keep].astype(np.int32), h[r, 1][keep], h[r, 2][keep].astype(np.int32)
+        seen += int(keep.sum())
+    assert seen == total, "sharded results do not cover every query exactly once"
     return fh, apv, nr
 
 
-def sharded_reduce(first_hit, ap, num_rel, counts, max_rank: int, num_g: int, group=None, denominators="valid"):
+def sharded_reduce(first_hit, ap, num_rel, counts, max_rank: int, num_g: int, group=None, denominators="valid", ids=None, total=None):
     """gather_per_query + the host reduction of utils/metrics.py:82-86 (same on every rank)."""
-    fh, apv, nr = gather_per_query(first_hit, ap, num_rel, counts, group)
+    fh, apv, nr = gather_per_query(first_hit, ap, num_rel, counts, group, ids=ids, total=total)
     return E.reduce_cmc_map(fh, apv, nr, max_rank, num_g, denominators)
 
 
@@ -142,18 +161,92 @@ def _allgather_rows(x_local: torch.Tensor, ids_all: list[torch.Tensor], N: int, 
     return full
 
 
-def rerank_sharded(prep_all: "E.Prepared", nq: int, k1: int, k2: int, lambda_value: float, precision=None, group=None,
-                   world: int | None = None, rank: int | None = None, exchange=None):
-    """utils/reranking.py:29-100 with the rows of the all-pairs matrix sharded over the ranks of `group`.
+def _allgather_contig(x_local: torch.Tensor, counts: list[int], group=None) -> torch.Tensor:
+    """All-gather contiguous row shards of unequal height -> [sum(counts), ...] in rank order."""
+    world = len(counts)
+    width = max(counts)
+    pad = x_local
+    if x_local.shape[0] != width:
+        pad = torch.zeros((width,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        pad[: x_local.shape[0]] = x_local
+    out = torch.empty((world * width,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    all_gather_into(out, pad.contiguous(), group)
+    if all(c == width for c in counts):
+        return out
+    return torch.cat([out[r * width: r * width + counts[r]] for r in range(world)], dim=0)
 
-    prep_all: the prepared stacked features (queries first) replicated on every rank.
-    Returns (final_local [Qs, G], (q_lo, q_hi)): the re-ranked distances of this rank's query rows.
-    `exchange` lets the tests substitute the all-gather (single-device emulation of several ranks).
-    """
+
+def rerank_owned_queries(nq: int, world: int, rank: int, device=None) -> torch.Tensor:
+    """Global indices of the query rows `rank` finishes in the fused row-sharded re-ranking: the rows of the 256-row
+    blocks p with p % world == rank (the blocks whose tiles that rank contracts: their [Q, G] block rows are local)."""
+    ids = torch.arange(nq, device=device)
+    return ids[(ids // 256) % world == rank]
+
+
+def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, world, rank):
+    """The fused (no N x N matrix) pipeline of reranking._rerank_fused with the tiles of the symmetric all-pairs pass
+    dealt out by 256-row block, cyclically.  Exchanges: thresholds [N] (all-gather), row maxima [N] (all-reduce max),
+    per-rank partial top-K keys [N, K] (all-gather, merged on every rank), V0 rows trimmed to their longest length
+    (all-gather).  Every rank finishes the query rows of its own blocks.  Same bits as the one-GPU fused pipeline.
+    Returns None if some neighbour list cannot be decided from the candidates (every rank sees the same flag)."""
+    from .reranking import FUSED_SAMPLE
     N = prep_all.n
     dev = prep_all.sqnorm.device
-    world = dist.get_world_size(group) if world is None else world
-    rank = dist.get_rank(group) if rank is None else rank
+    K = E.rerank_neighbor_count(k1, k2)
+    S = min(N, FUSED_SAMPLE)
+    t = min(K + 2, S)
+    counts = [shard_bounds(N, world, r)[1] - shard_bounds(N, world, r)[0] for r in range(world)]
+    lo, hi = shard_bounds(N, world, rank)
+    ids = (torch.arange(S, device=dev, dtype=torch.int64) * N) // S
+    smp = prep_all.take(ids)
+    dS = E.dist_matrix(prep_all.rows(lo, hi), smp, "sqeuclid", precision)
+    _, sval = E.row_topk(dS, t, None, want_values=True)
+    thr = _allgather_contig(sval[:, t - 1] + 1e-6 * (prep_all.sqnorm[lo:hi] + prep_all.sqnorm.max()), counts, group)
+    E.mark("rerank.thresholds")
+    expect = N * t / S
+    cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))
+    cand, cnt, block, col0, row_max = E.dist_symmetric_topk(prep_all, thr, cap, nq, precision, own_mod=world, own_rank=rank)
+    red = torch.cat([row_max, (cnt > cap).any().to(torch.float32).view(1)])
+    if _is_nccl(group):
+        dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)
+    else:
+        h = red.cpu(); dist.all_reduce(h, op=dist.ReduceOp.MAX, group=group); red.copy_(h)
+    row_max = red[:N].contiguous()
+    E.mark("rerank.all_pairs_gemm")
+    keys, _ = E.cand_topk(cand, cnt, K, row_max, thr, partial=True)
+    del cand
+    keys_all = torch.empty((world, N, K), dtype=torch.int64, device=dev)
+    all_gather_into(keys_all.view(-1), keys.view(-1), group)
+    nbr, nbr_val, status = E.merge_topk(keys_all, row_max, thr)
+    E.mark("rerank.topk")
+    row_ids = torch.arange(lo, hi, device=dev, dtype=torch.int32)
+    v0c, v0v, v0l = E.rerank_build_v0_sparse(row_ids, hi - lo, N, k1, nbr, nbr_val, row_max[lo:hi], prep_all.xn, prep_all.sqnorm)
+    info = torch.stack([v0l.max().to(torch.float32), status[0].to(torch.float32), red[N]])
+    if _is_nccl(group):
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+        info_h = info.cpu()
+    else:
+        info_h = info.cpu(); dist.all_reduce(info_h, op=dist.ReduceOp.MAX, group=group)
+    if float(info_h[1]) != 0.0 or float(info_h[2]) != 0.0:
+        return None
+    W = max(8, (int(info_h[0]) + 7) // 8 * 8)
+    W = min(W, v0c.shape[1])
+    v0_all = (_allgather_contig(v0c[:, :W].contiguous(), counts, group), _allgather_contig(v0v[:, :W].contiguous(), counts, group),
+              _allgather_contig(v0l, counts, group))
+    E.mark("rerank.v0")
+    q_ids = rerank_owned_queries(nq, world, rank, dev)
+    if q_ids.numel() == 0:
+        return torch.empty((0, N - nq), dtype=torch.float32, device=dev), q_ids
+    final = E.rerank_finish(nbr, v0_all, block, q_ids.to(torch.int32).contiguous(), row_max, N, nq, k1, k2, lambda_value,
+                            block_col0=col0, rows_global=True)
+    return final, q_ids
+
+
+def _rerank_sharded_plain(prep_all, nq, k1, k2, lambda_value, precision, group, world, rank, exchange=None):
+    """The materialising form: every rank contracts its own row block of the all-pairs matrix (its share of the query rows
+    followed by its share of the gallery rows), neighbour lists and V0 rows are all-gathered."""
+    N = prep_all.n
+    dev = prep_all.sqnorm.device
     ids_all = [rerank_row_ids(nq, N, world, r, dev) for r in range(world)]
     row_ids = ids_all[rank]
     q_lo, q_hi = shard_bounds(nq, world, rank)
@@ -164,16 +257,38 @@ def rerank_sharded(prep_all: "E.Prepared", nq: int, k1: int, k2: int, lambda_val
     rows = torch.empty((R, ld), dtype=torch.float32, device=dev)[:, :N]
     rm = torch.empty((R,), dtype=torch.float32, device=dev)
     E.dist_matrix(local, prep_all, "sqeuclid", precision, out=rows, row_max=rm)   # :36-41 + the maxima of :46
+    E.mark("rerank.all_pairs_gemm")
     K = E.rerank_neighbor_count(k1, k2)
     nbr_local = E.row_topk(rows, K, rm)                                           # :46-48
     gather = exchange or (lambda x: _allgather_rows(x, ids_all, N, group))
     nbr_all = gather(nbr_local)
+    E.mark("rerank.topk")
     ids32 = row_ids.to(torch.int32)
     v0 = E.rerank_build_v0(rows, ids32, N, k1, nbr_all, rm)                       # :51-71
     v0_all = tuple(gather(t) for t in v0)
+    E.mark("rerank.v0")
     q_ids = ids32[:nq_local].contiguous()
     final_local = E.rerank_finish(nbr_all, v0_all, rows[:nq_local], q_ids, rm[:nq_local], N, nq, k1, k2, lambda_value)  # :73-99
-    return final_local, (q_lo, q_hi)
+    return final_local, torch.arange(q_lo, q_hi, device=dev)
+
+
+def rerank_sharded(prep_all: "E.Prepared", nq: int, k1: int, k2: int, lambda_value: float, precision=None, group=None,
+                   world: int | None = None, rank: int | None = None, exchange=None):
+    """utils/reranking.py:29-100 with the work of the all-pairs pass and of the sparse stages sharded over the ranks of `group`.
+
+    prep_all: the prepared stacked features (queries first) replicated on every rank.
+    Returns (final_local [Qs, G], q_ids [Qs]): the re-ranked distances of the query rows this rank finished and their global
+    indices (256-row blocks dealt out cyclically in the fused form, one contiguous shard in the materialising form).
+    `exchange` lets the tests substitute the all-gather (single-device emulation of several ranks; materialising form only).
+    """
+    from .reranking import fused_enabled
+    world = dist.get_world_size(group) if world is None else world
+    rank = dist.get_rank(group) if rank is None else rank
+    if exchange is None and prep_all.xn is not None and fused_enabled(prep_all.n, precision):
+        out = _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, world, rank)
+        if out is not None:
+            return out
+    return _rerank_sharded_plain(prep_all, nq, k1, k2, lambda_value, precision, group, world, rank, exchange)
 
 
 # ------------------------------------------------------------------------------------------------

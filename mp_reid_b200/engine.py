@@ -152,7 +152,7 @@ def dist_matrix(q: Prepared, g: Prepared, metric: str = "sqeuclid", precision: s
     assert out.shape == (q.n, g.n) and out.stride(1) == 1 and out.dtype == torch.float32
     if met == L.ARCCOS:
         qa, ga = q.norm, g.norm
-    elif met == L.ONE_MINUS_DOT:
+    elif met in (L.ONE_MINUS_DOT, L.DOT):
         qa = ga = None
     else:
         qa, ga = q.sqnorm, g.sqnorm
@@ -188,7 +188,7 @@ def dist_matrix_all_pairs(x: Prepared, precision: str | None = None, out: torch.
     if out is None:
         out = alloc_dist(x.n, x.n, dev)
     assert out.shape == (x.n, x.n) and out.stride(1) == 1 and out.dtype == torch.float32
-    aux = x.norm if met == L.ARCCOS else (None if met == L.ONE_MINUS_DOT else x.sqnorm)
+    aux = x.norm if met == L.ARCCOS else (None if met in (L.ONE_MINUS_DOT, L.DOT) else x.sqnorm)
     if prec == L.FP32_SIMT:
         a, b, K, ldk = x.xn, None, x.D, x.xn.stride(0)
     elif prec == L.X3TF32:
@@ -409,9 +409,11 @@ def _operands(x: Prepared, prec: int):
     return x.bf, None
 
 
-def dist_symmetric_topk(x: Prepared, thr: torch.Tensor, cand_cap: int, query_num: int, precision: str | None = None):
+def dist_symmetric_topk(x: Prepared, thr: torch.Tensor, cand_cap: int, query_num: int, precision: str | None = None,
+                        own_mod: int = 1, own_rank: int = 0):
     """utils/reranking.py:36-48 without the matrix: -> (cand int64 [N, cap], cand_cnt int32 [N], block fp32 [Q, G] view,
-    col0 (column of gallery sample 0 in the block's buffer), row_max [N])."""
+    col0 (column of gallery sample 0 in the block's buffer), row_max [N]).
+    own_mod / own_rank: contract only the tiles of the 256-row blocks p with p % own_mod == own_rank (row-sharded runs)."""
     require_cuda()
     lib = L.load()
     prec = L.PRECISIONS[(precision or default_precision()).lower()]
@@ -431,21 +433,43 @@ def dist_symmetric_topk(x: Prepared, thr: torch.Tensor, cand_cap: int, query_num
     with torch.cuda.device(dev):
         L.check(lib.mpreid_dist_symmetric_topk(_ptr(a), _ptr(b), x.sqnorm.data_ptr(), _ptr(x.hscale), N, x.Dp, x.Dp, prec,
                                                thr.data_ptr(), cand.data_ptr(), cnt.data_ptr(), cand_cap, query_num,
-                                               block.data_ptr(), ld, row_max.data_ptr(), _stream()), "dist_symmetric_topk")
+                                               block.data_ptr(), ld, row_max.data_ptr(), own_mod, own_rank, _stream()), "dist_symmetric_topk")
     return cand, cnt, block, lead, row_max
 
 
-def cand_topk(cand: torch.Tensor, cnt: torch.Tensor, k: int, row_scale: torch.Tensor | None, thr: torch.Tensor):
-    """-> (idx int32 [N, k], val fp32 [N, k] (divided values), status int32[4] on the device)."""
+def cand_topk(cand: torch.Tensor, cnt: torch.Tensor, k: int, row_scale: torch.Tensor | None, thr: torch.Tensor, partial: bool = False):
+    """-> (idx int32 [N, k], val fp32 [N, k] (divided values), status int32[4] on the device); partial=True (one rank's
+    share of every row): -> (keys int64 [N, k], status)."""
     lib = L.load()
     N, cap = cand.shape
     dev = cand.device
+    status = torch.empty((4,), dtype=torch.int32, device=dev)
+    if partial:
+        keys = torch.empty((N, k), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.mpreid_cand_topk(cand.data_ptr(), cnt.data_ptr(), cap, N, k, _ptr(row_scale), thr.data_ptr(), None, None,
+                                         keys.data_ptr(), status.data_ptr(), _stream()), "cand_topk")
+        return keys, status
+    idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+    val = torch.empty((N, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mpreid_cand_topk(cand.data_ptr(), cnt.data_ptr(), cap, N, k, _ptr(row_scale), thr.data_ptr(), idx.data_ptr(),
+                                     val.data_ptr(), None, status.data_ptr(), _stream()), "cand_topk")
+    return idx, val, status
+
+
+def merge_topk(keys_all: torch.Tensor, row_scale: torch.Tensor | None, thr: torch.Tensor):
+    """keys_all int64 [P, N, k] (every rank's partial selection) -> (idx int32 [N, k], val fp32 [N, k], status int32[4])."""
+    lib = L.load()
+    P, N, k = keys_all.shape
+    dev = keys_all.device
     idx = torch.empty((N, k), dtype=torch.int32, device=dev)
     val = torch.empty((N, k), dtype=torch.float32, device=dev)
     status = torch.empty((4,), dtype=torch.int32, device=dev)
+    assert keys_all.is_contiguous()
     with torch.cuda.device(dev):
-        L.check(lib.mpreid_cand_topk(cand.data_ptr(), cnt.data_ptr(), cap, N, k, _ptr(row_scale), thr.data_ptr(), idx.data_ptr(),
-                                     val.data_ptr(), status.data_ptr(), _stream()), "cand_topk")
+        L.check(lib.mpreid_merge_topk(keys_all.data_ptr(), P, N, k, _ptr(row_scale), thr.data_ptr(), idx.data_ptr(), val.data_ptr(),
+                                      status.data_ptr(), _stream()), "merge_topk")
     return idx, val, status
 
 
@@ -471,14 +495,15 @@ def rerank_build_v0_sparse(row_ids: torch.Tensor | None, R: int, N: int, k1: int
 
 def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor,
                   N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None,
-                  block_col0: int | None = None) -> torch.Tensor:
+                  block_col0: int | None = None, rows_global: bool = False) -> torch.Tensor:
     """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q].
     block_col0: `dist_qrows` is instead the [Qs, >= col0 + G] buffer of query-to-gallery distances, gallery sample 0 at
-    column block_col0 (what the fused all-pairs pass keeps)."""
+    column block_col0 (what the fused all-pairs pass keeps).  rows_global: dist_qrows / row_max_q are the full [Q, .] block
+    and [N] maxima, addressed by the global indices q_ids (row-sharded runs).  The V0 arrays may be trimmed to any width."""
     require_cuda()
     lib = L.load()
     v0_col, v0_val, v0_len = v0
-    Qs = dist_qrows.shape[0]
+    Qs = int(q_ids.numel()) if rows_global else dist_qrows.shape[0]
     dev = dist_qrows.device
     if out is None:
         out = alloc_dist(Qs, N - Q, dev)
@@ -486,13 +511,13 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
     if nbytes == 0:
         raise ValueError(f"re_ranking: unsupported arguments N={N} Q={Q} k1={k1} k2={k2}")
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N
+    assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N and v0_col.shape == v0_val.shape
     col0 = Q if block_col0 is None else int(block_col0)
     with torch.cuda.device(dev):
         for stages in ((1, 2) if _timeline is not None else (3,)):   # timeline mode: the two halves as separate, timed calls
             L.check(lib.mpreid_rerank_finish_ex(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
                                                 dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
                                                 k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, stages,
-                                                _stream()), "rerank_finish")
+                                                v0_col.shape[1], int(bool(rows_global)), _stream()), "rerank_finish")
             mark("rerank.expand_index" if stages == 1 else "rerank.jaccard_blend")
     return out

@@ -152,6 +152,37 @@ class LazyDistmat:
     def __repr__(self):
         return f"LazyDistmat(shape={self.shape}, device={self._dev.device})"
 
+    def _row_blocks(self, rows):
+        t = self.device_tensor
+        for lo in range(0, self.shape[0], rows):
+            yield lo, t[lo:lo + rows]
+
+    def save(self, path: str, block_bytes: int = 256 << 20) -> str:
+        """Persist the matrix as a .npy file (the reference's TEST.DIST_MAT = "dist_mat.npy", config/defaults.py:327,
+        the on-disk format for offline analysis) without a second full-size host copy: the file is memory-mapped and
+        filled block by block straight from the device through one pinned staging buffer."""
+        if not path.endswith(".npy"):
+            path += ".npy"
+        out = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=self.shape)
+        if self._host is not None:
+            out[:] = self._host
+        else:
+            rows = max(1, block_bytes // max(4 * self.shape[1], 1))
+            stage = torch.empty((rows, self.shape[1]), dtype=torch.float32, pin_memory=True)
+            for lo, blk in self._row_blocks(rows):
+                n = blk.shape[0]
+                stage[:n].copy_(blk, non_blocking=True)
+                torch.cuda.current_stream(blk.device).synchronize()
+                out[lo:lo + n] = stage[:n].numpy()
+        out.flush()
+        del out
+        return path
+
+
+def load_distmat(path: str, mmap: bool = True) -> np.ndarray:
+    """Reads a matrix written by LazyDistmat.save / np.save (TEST.DIST_MAT)."""
+    return np.load(path, mmap_mode="r" if mmap else None)
+
 
 class LazyDistmatShards(LazyDistmat):
     """The same handle over query-row shards that live on several devices (single-process multi-GPU mode)."""
@@ -175,6 +206,13 @@ class LazyDistmatShards(LazyDistmat):
         if self._host is None:
             self._host = np.concatenate([t.cpu().numpy() for t in self._shards], axis=0)
         return self._host
+
+    def _row_blocks(self, rows):
+        base = 0
+        for t in self._shards:
+            for lo in range(0, t.shape[0], rows):
+                yield base + lo, t[lo:lo + rows]
+            base += t.shape[0]
 
     def __repr__(self):
         return f"LazyDistmatShards(shape={self.shape}, devices={[str(t.device) for t in self._shards]})"
@@ -442,7 +480,10 @@ class R1_mAP_eval():
                     flush(pend_rows // 32 * 32)
             qf = q.xn
         cmc, mAP = _eval_device(dist, q_pids, g_pids, q_camids, g_camids, 50, self._junk)  # :132 (max_rank is not forwarded)
-        return cmc, mAP, LazyDistmat(dist), self.pids, self.camids, qf, gf
+        lazy = LazyDistmat(dist)
+        if os.environ.get("MPREID_DIST_MAT"):   # TEST.DIST_MAT (config/defaults.py:327): keep the matrix for offline analysis
+            lazy.save(os.environ["MPREID_DIST_MAT"])
+        return cmc, mAP, lazy, self.pids, self.camids, qf, gf
 
     def _compute_multi(self, devs, q_pids, g_pids, q_camids, g_camids, norm):
         """Single-process multi-GPU evaluation: query rows are sharded over `devs`, every gallery

@@ -318,11 +318,78 @@ def make_sensitive_rerank(rm, rr):
           f"in {dt:.1f}s on {os.cpu_count()} cores")
 
 
+# --------------------------------------------------------------------------------------
+# the training-side distance workloads.  The reference's own loss code is executed on the CPU
+# (float32, and float64 for a tight gradient reference); nothing is copied: the source text is exec'd at run time
+# (loss/triplet_loss.py starts with a stray `from turtle import pd`, which needs tkinter and is skipped).
+def _exec_reference(rel_path, skip_prefixes=()):
+    lines = open(os.path.join(REF, rel_path)).read().split("\n")
+    code = "\n".join(l for l in lines if not any(l.startswith(p) for p in skip_prefixes))
+    ns = {}
+    exec(compile(code, f"<reference {rel_path}>", "exec"), ns)
+    return ns
+
+
+def make_losses():
+    os.makedirs(OUT, exist_ok=True)
+    tl = _exec_reference("loss/triplet_loss.py", skip_prefixes=("from turtle",))
+    sc = _exec_reference("loss/supcontrast.py")
+    out = {}
+    gen = torch.Generator("cpu").manual_seed(77)
+    # --- batch-hard triplet: P x K batches as the RandomIdentitySampler builds them (16 ids x 4), 16 x 4 and 8 x 8
+    for tag, (B, D, labels) in {
+        "pk": (64, 256, np.repeat(np.arange(16), 4)),
+        "pk8": (64, 96, np.repeat(np.arange(8), 8)),   # (the reference's mining needs equally many samples per label, :61-63)
+    }.items():
+        centers = torch.randn(int(labels.max()) + 1, D, generator=gen)
+        x = 0.35 * centers[torch.from_numpy(labels)] + torch.randn(B, D, generator=gen)   # weak clusters: some triplets violate the margin
+        out[f"tri_{tag}_x"] = x.numpy(); out[f"tri_{tag}_labels"] = labels.astype(np.int64)
+        for cfg_i, (margin, hard, norm) in enumerate([(None, 0.0, False), (0.3, 0.0, False), (0.3, 0.1, True), (None, 0.2, True)]):
+            for dt in (torch.float32, torch.float64):
+                xx = x.to(dt).clone().requires_grad_(True)
+                loss, d_ap, d_an = tl["TripletLoss"](margin, hard)(xx, torch.from_numpy(labels), normalize_feature=norm)
+                loss.backward()
+                k = f"tri_{tag}_{cfg_i}_{'f32' if dt == torch.float32 else 'f64'}"
+                out[k + "_loss"] = np.float64(loss.item())
+                if dt == torch.float64:   # the float64 run is the numerical reference (stored in float32: the bars are ~1e-5)
+                    out[k + "_ap"] = d_ap.detach().numpy().astype(np.float32)
+                    out[k + "_an"] = d_an.detach().numpy().astype(np.float32)
+                    out[k + "_grad"] = xx.grad.numpy().astype(np.float32)
+        d = tl["euclidean_dist"](x, x)
+        ap_, an_, pi, ni = tl["hard_example_mining"](d, torch.from_numpy(labels), return_inds=True)
+        out[f"tri_{tag}_pinds"] = pi.numpy(); out[f"tri_{tag}_ninds"] = ni.numpy()
+        out[f"tri_{tag}_dist_ap"] = ap_.numpy(); out[f"tri_{tag}_dist_an"] = an_.numpy()
+    out["tri_configs"] = np.array(json.dumps([[None, 0.0, False], [0.3, 0.0, False], [0.3, 0.1, True], [None, 0.2, True]]))
+    # --- stage-1 contrastive step: cached image features x prompt-learner text features of the batch's labels
+    for tag, (Bi, D, n_id) in {"b64": (64, 512, 20), "b200": (200, 256, 37)}.items():
+        target = torch.randint(0, n_id, (Bi,), generator=gen)
+        base = torch.nn.functional.normalize(torch.randn(n_id, D, generator=gen), dim=1)
+        # image features scatter around their identity's direction (cosine ~0.75), logits of a few units
+        img = torch.nn.functional.normalize(base[target] + (0.9 / D ** 0.5) * torch.randn(Bi, D, generator=gen), dim=1) * 3.0
+        txt = base[target] * 3.0 + 0.05 * torch.randn(Bi, D, generator=gen)
+        out[f"sc_{tag}_img"] = img.numpy(); out[f"sc_{tag}_txt"] = txt.numpy(); out[f"sc_{tag}_target"] = target.numpy()
+        for dt in (torch.float32, torch.float64):
+            i_, t_ = img.to(dt).clone().requires_grad_(True), txt.to(dt).clone().requires_grad_(True)
+            xent = sc["SupConLoss"]("cpu")
+            l1 = xent(i_, t_, target, target)            # processor/processor_uniprompt_stage1.py:88
+            l2 = xent(t_, i_, target, target)            # :89
+            (l1 + l2).backward()                         # :91-93
+            k = f"sc_{tag}_{'f32' if dt == torch.float32 else 'f64'}"
+            out[k + "_i2t"] = np.float64(l1.item()); out[k + "_t2i"] = np.float64(l2.item())
+            if dt == torch.float64:
+                out[k + "_grad_img"] = i_.grad.numpy().astype(np.float32); out[k + "_grad_txt"] = t_.grad.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+    print("[golden] losses: " + ", ".join(f"{k}={float(out[k]):.9f}" for k in sorted(out) if k.endswith("f32_loss") or k.endswith("f32_i2t")))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
+    ap.add_argument("--losses", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--full", default=None)
     a = ap.parse_args()
+    if a.losses:
+        make_losses()
     if a.small:
         make_small()
     if a.full:

@@ -50,11 +50,25 @@ lab = rng.randint(0, 40, 2300)
 feats = torch.from_numpy(centers[lab] + 1.3 * rng.randn(2300, 96).astype(np.float32)).to(dev)
 nq = 301
 prep = E.prep_rows(feats, normalize=True, keep_xn=False)
-for (k1, k2, lam) in [(20, 6, 0.3), (7, 1, 0.5)]:
-    want = _rerank_device(prep, nq, k1, k2, lam)
-    got, (lo, hi) = MD.rerank_sharded(prep, nq, k1, k2, lam)
-    assert (lo, hi) == MD.shard_bounds(nq, world, rank)
-    assert torch.equal(got, want[lo:hi]), (rank, k1, k2, float((got - want[lo:hi]).abs().max()))
+for fused in ("1", "0"):          # the fused (no N x N matrix) pipeline and the materialising one
+    os.environ["MPREID_RERANK_FUSED"] = fused
+    for (k1, k2, lam) in [(20, 6, 0.3), (7, 1, 0.5)]:
+        want = _rerank_device(prep, nq, k1, k2, lam)
+        got, ids = MD.rerank_sharded(prep, nq, k1, k2, lam)
+        if fused == "1":
+            assert torch.equal(ids, MD.rerank_owned_queries(nq, world, rank, dev))
+        else:
+            lo, hi = MD.shard_bounds(nq, world, rank)
+            assert torch.equal(ids.cpu(), torch.arange(lo, hi))
+        assert torch.equal(got, want[ids]), (rank, fused, k1, k2, float((got - want[ids]).abs().max()))
+        # per-query results gathered into global query order == one-GPU evaluation of the whole matrix
+        q_pid = torch.from_numpy(lab[:nq]).to(dev); g_pid = torch.from_numpy(lab[nq:]).to(dev)
+        fh, ap, nr = E.rank_eval(got, q_pid[ids], g_pid)
+        cmc, mAP = MD.sharded_reduce(fh, ap, nr, None, 50, 2300 - nq, ids=ids, total=nq)
+        fh0, ap0, nr0 = E.rank_eval(want, q_pid, g_pid)
+        cmc0, mAP0 = E.reduce_cmc_map(fh0.cpu().numpy(), ap0.cpu().numpy(), nr0.cpu().numpy(), 50, 2300 - nq)
+        assert mAP == mAP0 and np.array_equal(cmc, cmc0)
+os.environ.pop("MPREID_RERANK_FUSED")
 dist.barrier()
 if rank == 0:
     print("SHARDED_EVAL_OK", world)

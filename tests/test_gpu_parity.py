@@ -967,3 +967,115 @@ def test_jaccard_hash_kernel_equals_tile_kernel(monkeypatch):
         monkeypatch.delenv("MPREID_JACCARD")
         b = E.rerank_from_dist(dall, nq, k1, k2, 0.3, row_max=rm)
         assert torch.equal(a, b), (nq, ng, k1, k2, float((a - b).abs().max()))
+
+
+# ------------------------------------------------------------------------------------ training-side distance workloads
+def _losses(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "losses.npz")))
+
+
+@pytest.mark.parametrize("tag", ["pk", "pk8"])
+def test_triplet_loss_forward_backward_vs_reference(golden_dir, tag):
+    """loss/triplet_loss.py:TripletLoss executed by oracle/make_golden.py --losses (float64 run = numerical reference,
+    float32 run = what the reference trains with): loss, dist_ap / dist_an and d loss / d features under autograd."""
+    from mp_reid_b200 import triplet
+    g = _losses(golden_dir)
+    x = torch.from_numpy(g[f"tri_{tag}_x"]).to(DEV)
+    labels = torch.from_numpy(g[f"tri_{tag}_labels"]).to(DEV)
+    ap, an, pi, ni = triplet.batch_hard_distances(x, labels, return_inds=True)
+    assert np.array_equal(pi.cpu().numpy(), g[f"tri_{tag}_pinds"]) and np.array_equal(ni.cpu().numpy(), g[f"tri_{tag}_ninds"])
+    assert np.abs(ap.cpu().numpy() - g[f"tri_{tag}_dist_ap"]).max() <= 2e-5 and np.abs(an.cpu().numpy() - g[f"tri_{tag}_dist_an"]).max() <= 2e-5
+    for ci, (margin, hard, norm) in enumerate(json.loads(str(g["tri_configs"]))):
+        xx = x.clone().requires_grad_(True)
+        loss, d_ap, d_an = triplet.TripletLoss(margin, hard)(xx, labels, normalize_feature=norm)
+        loss.backward()
+        k = f"tri_{tag}_{ci}"
+        assert abs(float(loss) - float(g[k + "_f64_loss"])) <= 2e-5 * max(1.0, abs(float(g[k + "_f64_loss"]))), (k, float(loss))
+        assert abs(float(loss) - float(g[k + "_f32_loss"])) <= 5e-5 * max(1.0, abs(float(g[k + "_f32_loss"])))
+        assert np.abs(d_ap.detach().cpu().numpy() - g[k + "_f64_ap"]).max() <= 3e-5 * float(np.abs(g[k + "_f64_ap"]).max())
+        assert np.abs(d_an.detach().cpu().numpy() - g[k + "_f64_an"]).max() <= 3e-5 * float(np.abs(g[k + "_f64_an"]).max())
+        gref = g[k + "_f64_grad"]
+        assert np.abs(xx.grad.cpu().numpy() - gref).max() <= 2e-5 * float(np.abs(gref).max()) + 1e-9, (k, float(np.abs(xx.grad.cpu().numpy() - gref).max()))
+        assert float(np.abs(gref).max()) > 0
+
+
+def test_triplet_ragged_labels_and_determinism():
+    """Label groups of different sizes (the reference's mining cannot express them; checked against torch autograd on a
+    plain PyTorch restatement), a singleton label (its hardest positive is itself: clamp active, zero gradient), no
+    negatives at all, and bit-reproducibility of the atomics-free backward."""
+    from mp_reid_b200 import triplet
+    rs = np.random.RandomState(2)
+    labels = np.array([0] * 7 + [1] * 5 + [2] * 20 + [3] * 1 + [4] * 15)
+    x = torch.from_numpy((rs.randn(6, 80)[labels % 6] * 0.4 + rs.randn(len(labels), 80)).astype(np.float32)).to(DEV)
+    lab = torch.from_numpy(labels).to(DEV)
+
+    def torch_ref(xx):
+        d2 = (xx * xx).sum(1, keepdim=True) + (xx * xx).sum(1, keepdim=True).t() - 2 * xx @ xx.t()
+        d = d2.clamp(min=1e-12).sqrt()
+        same = lab[:, None] == lab[None, :]
+        ap = torch.where(same, d, torch.full_like(d, -float("inf"))).max(1).values
+        an = torch.where(~same, d, torch.full_like(d, float("inf"))).min(1).values
+        return ap, an
+
+    w_ap = torch.from_numpy(rs.rand(len(labels)).astype(np.float32)).to(DEV)
+    w_an = torch.from_numpy(rs.rand(len(labels)).astype(np.float32)).to(DEV)
+    grads = []
+    for fn in (lambda t: triplet.batch_hard_distances(t, lab), torch_ref, lambda t: triplet.batch_hard_distances(t, lab)):
+        xx = x.clone().double().requires_grad_(True) if fn is torch_ref else x.clone().requires_grad_(True)
+        ap, an = fn(xx)
+        ((ap * w_ap.to(ap.dtype)).sum() - (an * w_an.to(an.dtype)).sum()).backward()
+        grads.append((ap.detach().double().cpu().numpy(), an.detach().double().cpu().numpy(), xx.grad.double().cpu().numpy()))
+    assert np.abs(grads[0][0] - grads[1][0]).max() <= 2e-5 and np.abs(grads[0][1] - grads[1][1]).max() <= 2e-5
+    assert np.abs(grads[0][2] - grads[1][2]).max() <= 2e-5 * np.abs(grads[1][2]).max()
+    assert np.array_equal(grads[0][2], grads[2][2])                      # same bits on a second run
+    single = int(np.nonzero(labels == 3)[0][0])
+    assert grads[0][0][single] <= 2e-6                                   # singleton label: dist_ap is the clamped self distance
+    # no negatives at all
+    ap, an, pi, ni = triplet.batch_hard_distances(x[:5], torch.zeros(5, dtype=torch.int64, device=DEV), return_inds=True)
+    assert torch.isinf(an).all() and (ni == -1).all()
+
+
+@pytest.mark.parametrize("tag", ["b64", "b200"])
+def test_supcon_stage1_step_vs_reference(golden_dir, tag):
+    """processor/processor_uniprompt_stage1.py:88-93 with loss/supcontrast.py, executed by make_golden.py --losses: both
+    loss terms and the gradients with respect to image and text features; the one-directional SupConLoss module too."""
+    from mp_reid_b200 import supcon
+    g = _losses(golden_dir)
+    img = torch.from_numpy(g[f"sc_{tag}_img"]).to(DEV).requires_grad_(True)
+    txt = torch.from_numpy(g[f"sc_{tag}_txt"]).to(DEV).requires_grad_(True)
+    target = torch.from_numpy(g[f"sc_{tag}_target"]).to(DEV)
+    loss, i2t, t2i = supcon.stage1_contrastive_loss(img, txt, target, return_terms=True)
+    loss.backward()
+    k = f"sc_{tag}_f64"
+    assert abs(float(i2t) - float(g[k + "_i2t"])) <= 2e-5 and abs(float(t2i) - float(g[k + "_t2i"])) <= 2e-5
+    assert abs(float(loss) - float(g[k + "_i2t"]) - float(g[k + "_t2i"])) <= 4e-5
+    for got, want in ((img.grad, g[k + "_grad_img"]), (txt.grad, g[k + "_grad_txt"])):
+        assert np.abs(got.cpu().numpy() - want).max() <= 2e-5 * float(np.abs(want).max()) + 1e-8
+    # the module with the reference's signature: one direction, gradient only where it is needed (cached image features)
+    xent = supcon.SupConLoss("cuda")
+    t2 = txt.detach().clone().requires_grad_(True)
+    l1 = xent(img.detach(), t2, target, target) + xent(t2, img.detach(), target, target)
+    l1.backward()
+    assert abs(float(l1) - float(loss)) <= 1e-5
+    assert np.abs(t2.grad.cpu().numpy() - g[k + "_grad_txt"]).max() <= 2e-5 * float(np.abs(g[k + "_grad_txt"]).max()) + 1e-8
+    # tensor-core similarity (what large cached sets use) gives the same loss
+    l3 = supcon.stage1_contrastive_loss(img.detach(), txt.detach(), target, precision="3xfp16")
+    assert abs(float(l3) - float(loss)) <= 2e-5
+
+
+def test_distmat_persistence_round_trip(tmp_path, monkeypatch):
+    """TEST.DIST_MAT (config/defaults.py:327): the evaluator's matrix as a .npy file, written block by block."""
+    rng = np.random.RandomState(8)
+    Q, G, D = 70, 900, 64
+    x = torch.from_numpy(rng.randn(Q + G, D).astype(np.float32))
+    pid = rng.randint(0, 20, Q + G); cam = rng.randint(0, 4, Q + G)
+    path = str(tmp_path / "dist_mat.npy")
+    monkeypatch.setenv("MPREID_DIST_MAT", path)
+    ev = metrics.R1_mAP_eval(Q); ev.reset(); ev.update((x, pid, cam))
+    cmc, mAP, distmat, *_ = ev.compute()
+    back = metrics.load_distmat(path)
+    assert back.dtype == np.float32 and back.shape == (Q, G) and np.array_equal(np.asarray(back), np.asarray(distmat))
+    p2 = distmat.save(str(tmp_path / "again"), block_bytes=4 * G * 7)      # small blocks: several staged copies
+    assert p2.endswith(".npy") and np.array_equal(np.load(p2), np.asarray(distmat))
+    cmc2, mAP2 = metrics.eval_func(np.load(path), pid[:Q], pid[Q:], cam[:Q], cam[Q:])
+    assert mAP2 == mAP and np.array_equal(cmc, cmc2)
