@@ -169,6 +169,19 @@ MPREID_API int mpreid_rank_eval(const float* dist, int64_t ld_dist, int64_t Q, i
                      void* workspace, size_t workspace_bytes, int64_t pos_capacity,
                      int32_t* status, void* stream);
 
+/* The same from FEATURES in one call (what R1_mAP_eval.compute() runs between torch.cat and eval_func,
+ * utils/metrics.py:111-132): normalise (optional) + operand planes of both sides, distance matrix, ranking + CMC / AP,
+ * and optionally topk_idx [Q, topk] = the first topk columns of np.argsort(distmat, axis=1, kind='stable') (:39).
+ * qf [Q, D], gf [G, D] fp32.  The matrix goes to dist_out [Q, ld_dist_out] if given, else it lives in the workspace
+ * (size query: own_dist = 1).  status as for mpreid_rank_eval.                                                     */
+MPREID_API size_t mpreid_eval_features_workspace_bytes(int64_t Q, int64_t G, int64_t D, int precision, int64_t pos_capacity, int own_dist);
+MPREID_API int mpreid_eval_features(const float* qf, int64_t ld_q, const float* gf, int64_t ld_g, int64_t Q, int64_t G, int64_t D,
+                         int normalize, int metric, int precision,
+                         const int64_t* q_pid, const int64_t* g_pid, const int64_t* q_cam, const int64_t* g_cam, int junk_mode,
+                         int32_t* first_hit, double* ap, int32_t* num_rel,
+                         int32_t* topk_idx, int topk, float* dist_out, int64_t ld_dist_out,
+                         void* workspace, size_t workspace_bytes, int64_t pos_capacity, int32_t* status, void* stream);
+
 /* ---- per-row top-k ---------------------------------------------------------------------------
  * The first k entries of np.argsort(row / row_scale, kind='stable') (utils/reranking.py:46-48 with
  * k = k1+1; retrieval top-100).  row_scale may be NULL (no division).  idx [Q,k] int32, val [Q,k]
@@ -262,6 +275,24 @@ MPREID_API int mpreid_supcon_step(const float* S, int64_t ld_s, int64_t Ba, int6
                        const float* a, int64_t ld_a, const float* b, int64_t ld_b, int64_t D,
                        float* loss, float* grad_a, int64_t ld_ga, float* grad_b, int64_t ld_gb,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- multi-GPU surface for non-PyTorch consumers ---------------------------------------------
+ * Thin wrappers over NCCL (resolved at run time: dlopen("libnccl.so.2"), or the path in MPREID_NCCL_LIB), one
+ * communicator per process / GPU.  The path needs three collectives: the gallery broadcast, all-gathers (per-query
+ * results, neighbour lists, partial top-k keys, V0 rows) and a max all-reduce (row maxima of the sharded all-pairs pass).
+ * All buffers are device pointers; the calls are asynchronous on `stream`.
+ *   rank 0: mpreid_comm_unique_id(id) -> ship the 128 bytes to the other ranks out of band -> every rank, with ITS GPU
+ *   current: mpreid_comm_init(&comm, world, rank, id).  mpreid_comm_from_nccl adopts an existing ncclComm_t instead
+ *   (not destroyed by mpreid_comm_destroy).                                                                          */
+typedef struct mpreid_comm mpreid_comm;
+MPREID_API int mpreid_comm_unique_id(void* id_out_128_bytes);
+MPREID_API int mpreid_comm_init(mpreid_comm** comm, int world, int rank, const void* unique_id_128_bytes);
+MPREID_API int mpreid_comm_from_nccl(mpreid_comm** comm, void* nccl_comm, int world, int rank);
+MPREID_API int mpreid_comm_size(const mpreid_comm* comm, int* world, int* rank);
+MPREID_API int mpreid_comm_broadcast(mpreid_comm* comm, void* buf, size_t bytes, int root, void* stream);
+MPREID_API int mpreid_comm_allgather(mpreid_comm* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+MPREID_API int mpreid_comm_allreduce_max_f32(mpreid_comm* comm, float* buf, size_t count, void* stream);
+MPREID_API int mpreid_comm_destroy(mpreid_comm* comm);
 
 /* ---- host-side hooks (no GPU needed) -----------------------------------------------------------
  * The scalar arithmetic the kernels run is __host__ __device__ code; these two entry points run it

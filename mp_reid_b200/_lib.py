@@ -35,6 +35,9 @@ SIGNATURES = {
     "mpreid_dist_matrix_symmetric": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _p]),
     "mpreid_rank_eval_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mpreid_rank_eval": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _sz, _i64, _p, _p]),
+    "mpreid_eval_features_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i64, _i32]),
+    "mpreid_eval_features": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i64,
+                                    _p, _sz, _i64, _p, _p]),
     "mpreid_row_topk": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
     "mpreid_row_max": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "mpreid_rerank_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
@@ -54,6 +57,14 @@ SIGNATURES = {
     "mpreid_triplet_backward": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "mpreid_supcon_workspace_bytes": (_sz, [_i64, _i64]),
     "mpreid_supcon_step": (_i32, [_p, _i64, _i64, _i64, _p, _p, _f32, _i32, _f32, _f32, _p, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _sz, _p]),
+    "mpreid_comm_unique_id": (_i32, [_p]),
+    "mpreid_comm_init": (_i32, [C.POINTER(_p), _i32, _i32, _p]),
+    "mpreid_comm_from_nccl": (_i32, [C.POINTER(_p), _p, _i32, _i32]),
+    "mpreid_comm_size": (_i32, [_p, C.POINTER(_i32), C.POINTER(_i32)]),
+    "mpreid_comm_broadcast": (_i32, [_p, _p, _sz, _i32, _p]),
+    "mpreid_comm_allgather": (_i32, [_p, _p, _p, _sz, _p]),
+    "mpreid_comm_allreduce_max_f32": (_i32, [_p, _p, _sz, _p]),
+    "mpreid_comm_destroy": (_i32, [_p]),
     "mpreid_host_average_precision": (C.c_double, [_p, _i32, _i64]),
     "mpreid_host_order_keys": (None, [_p, _i64, _p]),
 }

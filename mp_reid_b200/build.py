@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpreid_b200.so")
-SOURCES = ["api.cu", "prep.cu", "dist_simt.cu", "dist_tc.cu", "rank_eval.cu", "topk.cu", "rerank.cu", "mining.cu", "triplet.cu", "supcon.cu"]
+SOURCES = ["api.cu", "prep.cu", "dist_simt.cu", "dist_tc.cu", "rank_eval.cu", "topk.cu", "rerank.cu", "mining.cu", "triplet.cu", "supcon.cu", "comm.cu", "eval_features.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out.strip():
             print(out)
         objs.append(obj)
-    link = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    link = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

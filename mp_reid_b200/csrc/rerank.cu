@@ -1072,13 +1072,14 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
   const int Keff = (int)(K < N ? K : N);
   const int32_t* v_col = v0_col; const uint16_t* v_val = v0_val; const int32_t* v_len = v0_len;
   if (k2 != 1) { v_col = w.v_col; v_val = w.v_val; v_len = w.v_len; }
+  const int v0s = (int)(v0_stride > 0 ? v0_stride : w.C0);   // row stride of the V0 arrays (the capacity, or a trimmed width)
+  const int64_t vstride = k2 != 1 ? w.C1 : (int64_t)v0s;      // row stride of V (== V0 when there is no query expansion)
   if (stages & 1) {
     // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
     if (k2 != 1) {
       // rows whose k2 gathered V0 rows hold <= 512 entries: one warp each; the rest (large k1 / k2): one CTA each
       const int k2e = k2 < Keff ? k2 : Keff;
       const int64_t wgrid = ceil_div(N, kQeWarps) < (int64_t)sms * 6 ? ceil_div(N, kQeWarps) : (int64_t)sms * 6;
-      const int v0s = (int)(v0_stride > 0 ? v0_stride : w.C0);   // row stride of the V0 arrays (the capacity, or a trimmed width)
       k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
                                                                    w.v_col, w.v_val, w.v_len, w.C1);
       const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
@@ -1089,9 +1090,9 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
     const int rows_per_cta = 8;
     const unsigned csc_grid = (unsigned)ceil_div(N - Q, rows_per_cta);
-    k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, w.C1, w.col_cnt);
+    k_csc_count<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_len, vstride, w.col_cnt);
     k_scan_i64<<<1, 1024, 0, st>>>(w.col_cnt, w.col_off, N);
-    k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, w.C1, w.col_off, w.col_fill, w.csc_row, w.csc_val);
+    k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, vstride, w.col_off, w.col_fill, w.csc_row, w.csc_val);
     MPREID_CUDA_CHECK(cudaGetLastError());
   }
   if (!(stages & 2)) return MPREID_OK;
@@ -1121,7 +1122,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     const int64_t items = Qs * n_tiles;
     const int64_t jac_grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
     k_jaccard_sparse<<<(unsigned)jac_grid, jac_threads, jac_smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
-                                                                        v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                        v_col, v_val, v_len, vstride, w.col_off, w.csc_row, w.csc_val, final_dist,
                                                                         ld_final, tile_cols, (int)n_tiles, rows_global);
   } else {
     // bucket kernel: the whole gallery in one tile when it fits next to the 48 KB entry buffers (up to ~88,000 gallery
@@ -1138,7 +1139,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     const int64_t items = Qs * n_tiles;
     const int64_t grid = items < (int64_t)sms * ctas_per_sm ? items : (int64_t)sms * ctas_per_sm;
     k_jaccard_bucket<<<(unsigned)grid, kJacBWarps * 32, smem, st>>>(dist_q, ld_dist, col0, q_ids, (int)Qs, (int)N, (int)Q, lambda_value, row_max_q,
-                                                                    v_col, v_val, v_len, w.C1, w.col_off, w.csc_row, w.csc_val, final_dist,
+                                                                    v_col, v_val, v_len, vstride, w.col_off, w.csc_row, w.csc_val, final_dist,
                                                                     ld_final, tile_cols, (int)n_tiles, rows_global);
   }
   MPREID_CUDA_CHECK(cudaGetLastError());

@@ -9,6 +9,8 @@ arrays in global query order, which makes the N-GPU result bit-identical to the 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -227,6 +229,9 @@ def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, 
         info_h = info.cpu()
     else:
         info_h = info.cpu(); dist.all_reduce(info_h, op=dist.ReduceOp.MAX, group=group)
+    if os.environ.get("MPREID_DEBUG"):
+        print(f"[rerank_sharded rank {rank}] max V0 length {float(info_h[0])}, undecided rows {float(info_h[1])}, list overflow {float(info_h[2])}, "
+              f"longest list {int(cnt.max())} of {cap}", flush=True)
     if float(info_h[1]) != 0.0 or float(info_h[2]) != 0.0:
         return None
     W = max(8, (int(info_h[0]) + 7) // 8 * 8)

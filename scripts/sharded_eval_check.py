@@ -49,7 +49,7 @@ centers = rng.randn(40, 96).astype(np.float32)
 lab = rng.randint(0, 40, 2300)
 feats = torch.from_numpy(centers[lab] + 1.3 * rng.randn(2300, 96).astype(np.float32)).to(dev)
 nq = 301
-prep = E.prep_rows(feats, normalize=True, keep_xn=False)
+prep = E.prep_rows(feats, normalize=True, keep_xn=True)   # the fused pipelines read feature rows
 for fused in ("1", "0"):          # the fused (no N x N matrix) pipeline and the materialising one
     os.environ["MPREID_RERANK_FUSED"] = fused
     for (k1, k2, lam) in [(20, 6, 0.3), (7, 1, 0.5)]:
@@ -69,6 +69,31 @@ for fused in ("1", "0"):          # the fused (no N x N matrix) pipeline and the
         cmc0, mAP0 = E.reduce_cmc_map(fh0.cpu().numpy(), ap0.cpu().numpy(), nr0.cpu().numpy(), 50, 2300 - nq)
         assert mAP == mAP0 and np.array_equal(cmc, cmc0)
 os.environ.pop("MPREID_RERANK_FUSED")
+# ---- the C-ABI communicator (mpreid_comm_*): the three collectives of the path between the ranks, without torch.distributed
+if backend == "nccl":
+    import ctypes
+    from mp_reid_b200 import _lib as L
+    lib = L.load()
+    uid = ctypes.create_string_buffer(128)
+    if rank == 0:
+        L.check(lib.mpreid_comm_unique_id(uid), "comm_unique_id")
+    box = [uid.raw]
+    dist.broadcast_object_list(box, src=0)          # the 128 bytes travel out of band
+    uid = ctypes.create_string_buffer(box[0], 128)
+    comm = ctypes.c_void_p()
+    L.check(lib.mpreid_comm_init(ctypes.byref(comm), world, rank, uid), "comm_init")
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.full((4096,), float(rank + 1), device=dev) if rank == 0 else torch.zeros(4096, device=dev)
+    L.check(lib.mpreid_comm_broadcast(comm, g.data_ptr(), g.numel() * 4, 0, st), "comm_broadcast")
+    mine = torch.full((512,), float(rank), device=dev)
+    allv = torch.empty((world, 512), device=dev)
+    L.check(lib.mpreid_comm_allgather(comm, mine.data_ptr(), allv.data_ptr(), 512 * 4, st), "comm_allgather")
+    mx = torch.arange(100, dtype=torch.float32, device=dev) * (1.0 if rank == 0 else -1.0)
+    L.check(lib.mpreid_comm_allreduce_max_f32(comm, mx.data_ptr(), 100, st), "comm_allreduce_max_f32")
+    torch.cuda.synchronize()
+    assert bool((g == 1.0).all()) and all(bool((allv[r] == float(r)).all()) for r in range(world))
+    assert torch.equal(mx, torch.arange(100, dtype=torch.float32, device=dev))
+    L.check(lib.mpreid_comm_destroy(comm), "comm_destroy")
 dist.barrier()
 if rank == 0:
     print("SHARDED_EVAL_OK", world)

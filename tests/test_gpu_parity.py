@@ -1079,3 +1079,73 @@ def test_distmat_persistence_round_trip(tmp_path, monkeypatch):
     assert p2.endswith(".npy") and np.array_equal(np.load(p2), np.asarray(distmat))
     cmc2, mAP2 = metrics.eval_func(np.load(path), pid[:Q], pid[Q:], cam[:Q], cam[Q:])
     assert mAP2 == mAP and np.array_equal(cmc, cmc2)
+
+
+# ------------------------------------------------------------------------------------ C-ABI completion
+def test_eval_features_single_c_call_equals_layered_path():
+    """mpreid_eval_features: features -> (first_hit, AP, num_rel[, top-k indices, matrix]) in ONE C call, against the layered
+    path (prep_rows + dist_matrix + rank_eval + row_topk) the Python evaluator drives: bit-identical."""
+    import ctypes
+    from mp_reid_b200 import _lib as L
+    lib = L.load()
+    qf, gf, q_pid, g_pid, q_cam, g_cam = synth.make_set(333, 5001, 200, 70, 5, seed=51, sigma=2.0, cross_modality=True)
+    q, g = qf.to(DEV), gf.to(DEV)
+    lab = [torch.from_numpy(a).to(DEV) for a in (q_pid, g_pid, q_cam, g_cam)]
+    Q, G, D = q.shape[0], g.shape[0], q.shape[1]
+    for prec_name, metric_name, junk_name in [("3xfp16", "sqeuclid", "none"), ("3xtf32", "arccos", "pid_cam"), ("simt", "one_minus_dot", "pid_cam"),
+                                              ("bf16", "sqeuclid", "none")]:
+        prec, metric, junk = L.PRECISIONS[prec_name], L.METRICS[metric_name], L.JUNKS[junk_name]
+        cap = 1 << 18
+        nbytes = lib.mpreid_eval_features_workspace_bytes(Q, G, D, prec, cap, 1)
+        assert nbytes > 0
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=DEV)
+        res = E.RankResult(Q, DEV)
+        topk = torch.empty((Q, 37), dtype=torch.int32, device=DEV)
+        L.check(lib.mpreid_eval_features(q.data_ptr(), q.stride(0), g.data_ptr(), g.stride(0), Q, G, D, 1, metric, prec,
+                                         lab[0].data_ptr(), lab[1].data_ptr(), lab[2].data_ptr(), lab[3].data_ptr(), junk,
+                                         res.first_hit.data_ptr(), res.ap.data_ptr(), res.num_rel.data_ptr(), topk.data_ptr(), 37, None, 0,
+                                         ws.data_ptr(), nbytes, cap, res.status.data_ptr(), torch.cuda.current_stream().cuda_stream), "eval_features")
+        fh, ap, nr, st = res.to_host()
+        assert int(st[0]) == 0
+        pq = E.prep_rows(q, normalize=True, precision=prec_name); pg = E.prep_rows(g, normalize=True, precision=prec_name)
+        d = E.dist_matrix(pq, pg, metric_name, prec_name)
+        fh0, ap0, nr0 = E.rank_eval_host(d, q_pid, g_pid, q_cam, g_cam, junk_name)
+        assert np.array_equal(fh, fh0) and np.array_equal(ap, ap0) and np.array_equal(nr, nr0), (prec_name, metric_name)
+        assert torch.equal(topk, E.row_topk(d, 37))
+    # the matrix can be handed back too
+    dist = E.alloc_dist(Q, G, DEV)
+    nbytes = lib.mpreid_eval_features_workspace_bytes(Q, G, D, L.X3FP16, 1 << 18, 0)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=DEV)
+    res = E.RankResult(Q, DEV)
+    L.check(lib.mpreid_eval_features(q.data_ptr(), q.stride(0), g.data_ptr(), g.stride(0), Q, G, D, 1, L.SQEUCLID, L.X3FP16,
+                                     lab[0].data_ptr(), lab[1].data_ptr(), None, None, L.JUNK_NONE,
+                                     res.first_hit.data_ptr(), res.ap.data_ptr(), res.num_rel.data_ptr(), None, 0, dist.data_ptr(), dist.stride(0),
+                                     ws.data_ptr(), nbytes, 1 << 18, res.status.data_ptr(), torch.cuda.current_stream().cuda_stream), "eval_features")
+    pq = E.prep_rows(q, normalize=True); pg = E.prep_rows(g, normalize=True)
+    assert torch.equal(dist, E.dist_matrix(pq, pg))
+
+
+def test_comm_c_abi_single_rank():
+    """mpreid_comm_* (NCCL through the C ABI, resolved with dlopen): a one-rank communicator exercises every entry
+    point on the one-GPU test box; the two-rank exchange is part of scripts/sharded_eval_check.py under NCCL."""
+    import ctypes
+    from mp_reid_b200 import _lib as L
+    lib = L.load()
+    uid = ctypes.create_string_buffer(128)
+    L.check(lib.mpreid_comm_unique_id(uid), "comm_unique_id")
+    comm = ctypes.c_void_p()
+    torch.cuda.set_device(0)
+    L.check(lib.mpreid_comm_init(ctypes.byref(comm), 1, 0, uid), "comm_init")
+    world, rank = ctypes.c_int(-1), ctypes.c_int(-1)
+    L.check(lib.mpreid_comm_size(comm, ctypes.byref(world), ctypes.byref(rank)), "comm_size")
+    assert (world.value, rank.value) == (1, 0)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.arange(1000, dtype=torch.float32, device=DEV)
+    y = torch.empty_like(x)
+    L.check(lib.mpreid_comm_broadcast(comm, x.data_ptr(), x.numel() * 4, 0, st), "comm_broadcast")
+    L.check(lib.mpreid_comm_allgather(comm, x.data_ptr(), y.data_ptr(), x.numel() * 4, st), "comm_allgather")
+    L.check(lib.mpreid_comm_allreduce_max_f32(comm, y.data_ptr(), y.numel(), st), "comm_allreduce_max_f32")
+    torch.cuda.synchronize()
+    assert torch.equal(x, torch.arange(1000, dtype=torch.float32, device=DEV)) and torch.equal(x, y)
+    L.check(lib.mpreid_comm_destroy(comm), "comm_destroy")
+    assert lib.mpreid_comm_broadcast(None, x.data_ptr(), 4, 0, st) != 0      # null communicator -> error code, no crash
