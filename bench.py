@@ -326,11 +326,22 @@ def run_ours(args, data, workload, wkey):
             return results
         out = torch.empty((world, steps, slot_bytes), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(out.view(-1), dev_slots[:steps].reshape(-1))
-        if rank != 0:
-            return None
-        h = out.cpu().numpy()
-        counts = [MD.shard_bounds(Qall, world, r)[1] - MD.shard_bounds(Qall, world, r)[0] for r in range(world)] if strong else [Q] * world
-        return [reduce_host([unpack(h[r, s], counts[r]) for r in range(world)]) for s in range(steps)]
+        # every rank now holds every step's per-query results: the host reductions (numpy, global query order) are dealt out
+        # over the ranks (step s on rank s % N) instead of queueing on rank 0's one host thread; the (cmc, mAP) of all
+        # steps then meet on every rank with one tiny all-reduce
+        mine = [s for s in range(steps) if s % world == rank]
+        res = torch.zeros((steps, 51), dtype=torch.float64, device=dev)
+        if mine:
+            h = out[:, mine].cpu().numpy()
+            counts = [MD.shard_bounds(Qall, world, r)[1] - MD.shard_bounds(Qall, world, r)[0] for r in range(world)] if strong else [Q] * world
+            vals = np.zeros((len(mine), 51))
+            for k, s in enumerate(mine):
+                cmc, mAP = reduce_host([unpack(h[r, k], counts[r]) for r in range(world)])
+                vals[k, : len(cmc)] = cmc; vals[k, 50] = mAP
+            res[mine] = torch.from_numpy(vals).to(dev)
+        dist.all_reduce(res)
+        rh = res.cpu().numpy()
+        return [(rh[s, :50].astype(np.float32), np.float64(rh[s, 50])) for s in range(steps)]
 
     # ---- e2e inputs
     if distributed:

@@ -230,8 +230,10 @@ MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                          float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream);
 /* General form of mpreid_rerank_finish: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the
  * all-pairs matrix; the pad (Q & 31) for the [Q, G] block mpreid_dist_symmetric_topk keeps; ld_dist >= col0 + N-Q),
- * and the two halves may run as separate calls on the same workspace: stages 1 = query expansion + inverted index
- * (:73-82), 2 = Jaccard + blend (:84-99), 3 = both.
+ * and the parts may run as separate calls on the same workspace: stages is a mask of 1 = query expansion + inverted index
+ * (:73-82), 2 = sparse Jaccard accumulation and blend of the touched entries (:84-95), 4 = the dense default blend (:95
+ * with temp_min = 0; needs only the distance block and the maxima, so it may run early on another stream; 2 must come
+ * after 4); 7 = everything.
  * v0_stride: row stride of v0_col / v0_val in entries (0 = mpreid_rerank_v0_capacity; a sharded run all-gathers the V0
  * rows trimmed to their longest length).  rows_global != 0: dist_q and row_max_q are addressed by the GLOBAL query index
  * q_ids[il] (the [Q, .] block and the [N] maxima a rank holds in the row-sharded form) instead of the local row il.   */
@@ -240,6 +242,10 @@ MPREID_API int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int3
                             int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                             float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
                             int64_t v0_stride, int rows_global, void* stream);
+/* Stage 4 alone: final[il, c] = fp16(1 - lambda) + lambda * dist_q[row(il), col0 + c] / row_max_q[row(il)], row(il) =
+ * src_rows[il] if given (global addressing) else il.  Needs nothing from the sparse stages.                         */
+MPREID_API int mpreid_rerank_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
+                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);

@@ -1048,6 +1048,18 @@ extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int
 
 namespace mpreid {
 
+static int launch_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
+                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, cudaStream_t st) {
+  const int sms = sm_count_of_current_device();
+  const bool vec = (((uintptr_t)(dist_q + col0) | (uintptr_t)final_dist) & 15) == 0 && ld_dist % 4 == 0 && ld_final % 4 == 0;
+  const int64_t work = Qs * ceil_div(G, kBlendThreads * kBlendPer);
+  const int64_t grid = work < (int64_t)sms * 16 ? work : (int64_t)sms * 16;
+  if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
+  else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
 // :73-99 for the query rows dist_q[Qs, ...]: dist_q[il, col0 + c] is the distance of query row il to gallery sample c
 static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                               const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
@@ -1055,7 +1067,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
                               float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, int64_t v0_stride,
                               int rows_global, cudaStream_t st) {
   MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_q && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
-  MPREID_REQUIRE(stages >= 1 && stages <= 3, "rerank_finish: stages must be 1 (expand + index), 2 (Jaccard + blend) or 3 (both)");
+  MPREID_REQUIRE(stages >= 1 && stages <= 7, "rerank_finish: stages is a mask of 1 (expand + index), 2 (sparse Jaccard), 4 (default blend)");
   MPREID_REQUIRE(!rows_global || q_ids, "rerank_finish: rows_global needs q_ids");
   MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= col0 + (N - Q) && ld_final >= N - Q,
                  "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
@@ -1095,17 +1107,14 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
     k_csc_fill<<<csc_grid, rows_per_cta * 32, 0, st>>>((int)N, (int)Q, v_col, v_val, v_len, vstride, w.col_off, w.col_fill, w.csc_row, w.csc_val);
     MPREID_CUDA_CHECK(cudaGetLastError());
   }
-  if (!(stages & 2)) return MPREID_OK;
+  if (!(stages & 6)) return MPREID_OK;
   // :84-99  dense default, then the sparse accumulation over the touched entries
   const int64_t G = N - Q;
-  {
-    const bool vec = (((uintptr_t)(dist_q + col0) | (uintptr_t)final_dist) & 15) == 0 && ld_dist % 4 == 0 && ld_final % 4 == 0;
-    const int64_t work = Qs * ceil_div(G, kBlendThreads * kBlendPer);
-    const int64_t grid = work < (int64_t)sms * 16 ? work : (int64_t)sms * 16;
-    const int32_t* src_rows = rows_global ? q_ids : nullptr;
-    if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
-    else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
+  if (stages & 4) {
+    const int rc = launch_blend_default(dist_q, ld_dist, col0, rows_global ? q_ids : nullptr, row_max_q, Qs, G, lambda_value, final_dist, ld_final, st);
+    if (rc != MPREID_OK) return rc;
   }
+  if (!(stages & 2)) return MPREID_OK;
   const char* jac_env = getenv("MPREID_JACCARD");          // "tile": the per-step-barrier kernel (tests / comparison)
   if (jac_env && jac_env[0] == 't') {
     // tile: at most 41,600 gallery entries (81 KB) so that two 512-thread CTAs share an SM at MSMT17 size; a gallery
@@ -1153,12 +1162,21 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                                     int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                                     float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qrows, ld_dist, Q, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, 3, 0, 0, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, 7, 0, 0, (cudaStream_t)stream);
+}
+
+// The dense default blend alone (stage 4 of mpreid_rerank_finish_ex without any of the sparse-stage arguments).
+extern "C" int mpreid_rerank_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
+                                           int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, void* stream) {
+  MPREID_REQUIRE(dist_q && row_max_q && final_dist && Qs > 0 && G > 0 && col0 >= 0 && ld_dist >= col0 + G && ld_final >= G && Qs < INT32_MAX && G < INT32_MAX,
+                 "rerank_blend_default: bad arguments");
+  return launch_blend_default(dist_q, ld_dist, col0, src_rows, row_max_q, Qs, G, lambda_value, final_dist, ld_final, (cudaStream_t)stream);
 }
 
 // General form: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the all-pairs matrix, 0 or the
 // alignment pad for the [Qs, G] block the fused all-pairs pass keeps), and the two halves can run as separate calls
-// on the same workspace (stages 1 = query expansion + inverted index, 2 = Jaccard + blend, 3 = both).
+// on the same workspace (stages: mask of 1 = query expansion + inverted index, 2 = sparse Jaccard accumulation over the
+// touched entries, 4 = the dense default blend; 4 depends on nothing but the distance block and may run early, on another stream).
 extern "C" int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int32_t* v0_col, const uint16_t* v0_val, const int32_t* v0_len,
                                        const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                                        int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,

@@ -242,8 +242,8 @@ def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, 
     q_ids = rerank_owned_queries(nq, world, rank, dev)
     if q_ids.numel() == 0:
         return torch.empty((0, N - nq), dtype=torch.float32, device=dev), q_ids
-    final = E.rerank_finish(nbr, v0_all, block, q_ids.to(torch.int32).contiguous(), row_max, N, nq, k1, k2, lambda_value,
-                            block_col0=col0, rows_global=True)
+    q32 = q_ids.to(torch.int32).contiguous()
+    final = E.rerank_finish(nbr, v0_all, block, q32, row_max, N, nq, k1, k2, lambda_value, block_col0=col0, rows_global=True)
     return final, q_ids
 
 

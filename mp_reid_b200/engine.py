@@ -493,9 +493,16 @@ def rerank_build_v0_sparse(row_ids: torch.Tensor | None, R: int, N: int, k1: int
     return v0_col, v0_val, v0_len
 
 
+def rerank_finish_workspace(N: int, Q: int, k1: int, k2: int, device) -> torch.Tensor:
+    nbytes = L.load().mpreid_rerank_finish_workspace_bytes(N, Q, k1, k2)
+    if nbytes == 0:
+        raise ValueError(f"re_ranking: unsupported arguments N={N} Q={Q} k1={k1} k2={k2}")
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device)
+
+
 def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor,
                   N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None,
-                  block_col0: int | None = None, rows_global: bool = False) -> torch.Tensor:
+                  block_col0: int | None = None, rows_global: bool = False, stages: int = 7, ws: torch.Tensor | None = None) -> torch.Tensor:
     """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q].
     block_col0: `dist_qrows` is instead the [Qs, >= col0 + G] buffer of query-to-gallery distances, gallery sample 0 at
     column block_col0 (what the fused all-pairs pass keeps).  rows_global: dist_qrows / row_max_q are the full [Q, .] block
@@ -510,14 +517,32 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
     nbytes = lib.mpreid_rerank_finish_workspace_bytes(N, Q, k1, k2)
     if nbytes == 0:
         raise ValueError(f"re_ranking: unsupported arguments N={N} Q={Q} k1={k1} k2={k2}")
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    if ws is None:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N and v0_col.shape == v0_val.shape
     col0 = Q if block_col0 is None else int(block_col0)
     with torch.cuda.device(dev):
-        for stages in ((1, 2) if _timeline is not None else (3,)):   # timeline mode: the two halves as separate, timed calls
+        parts = [stages] if _timeline is None else [p for p in (stages & 1, stages & 6) if p]   # timeline mode: separately timed calls
+        for part in parts:
             L.check(lib.mpreid_rerank_finish_ex(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
                                                 dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
-                                                k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, stages,
+                                                k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, part,
                                                 v0_col.shape[1], int(bool(rows_global)), _stream()), "rerank_finish")
-            mark("rerank.expand_index" if stages == 1 else "rerank.jaccard_blend")
+            if part == 1:
+                mark("rerank.expand_index")
+            elif part & 2:
+                mark("rerank.jaccard_blend")
     return out
+
+
+def rerank_blend_default(dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor, N: int, Q: int, lambda_value: float,
+                         out: torch.Tensor, block_col0: int | None = None, rows_global: bool = False):
+    """The dense part of utils/reranking.py:95 (Jaccard distance 1 wherever the query shares no V column with the gallery
+    sample): depends only on the distance block and the maxima, so it can run on a side stream while the sparse stages run."""
+    lib = L.load()
+    Qs = int(q_ids.numel()) if rows_global else dist_qrows.shape[0]
+    col0 = Q if block_col0 is None else int(block_col0)
+    with torch.cuda.device(out.device):
+        L.check(lib.mpreid_rerank_blend_default(dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids) if rows_global else None,
+                                                row_max_q.data_ptr(), Qs, N - Q, float(lambda_value), out.data_ptr(), out.stride(0), _stream()),
+                "rerank_blend_default")
