@@ -243,9 +243,10 @@ MPREID_API int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int3
                             float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
                             int64_t v0_stride, int rows_global, void* stream);
 /* Stage 4 alone: final[il, c] = fp16(1 - lambda) + lambda * dist_q[row(il), col0 + c] / row_max_q[row(il)], row(il) =
- * src_rows[il] if given (global addressing) else il.  Needs nothing from the sparse stages.                         */
+ * src_rows[il] if given (global addressing) else il.  Needs nothing from the sparse stages.  ctas_per_sm > 0 caps the
+ * launch to that many 256-thread CTAs per SM (a background launch next to latency-bound kernels); 0 = full occupancy. */
 MPREID_API int mpreid_rerank_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
-                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, void* stream);
+                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, int ctas_per_sm, void* stream);
 MPREID_API int mpreid_rerank(const float* dist, int64_t ld_dist, const float* row_max_in, int64_t N, int64_t Q, int k1, int k2,
                   float lambda_value, float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes,
                   int32_t* status, void* stream);

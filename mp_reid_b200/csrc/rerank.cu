@@ -1049,11 +1049,13 @@ extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int
 namespace mpreid {
 
 static int launch_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
-                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, cudaStream_t st) {
+                                int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, int ctas_per_sm, cudaStream_t st) {
   const int sms = sm_count_of_current_device();
   const bool vec = (((uintptr_t)(dist_q + col0) | (uintptr_t)final_dist) & 15) == 0 && ld_dist % 4 == 0 && ld_final % 4 == 0;
   const int64_t work = Qs * ceil_div(G, kBlendThreads * kBlendPer);
-  const int64_t grid = work < (int64_t)sms * 16 ? work : (int64_t)sms * 16;
+  // persistent grid; ctas_per_sm > 0 caps the footprint (a background launch that shares the SMs with latency-bound kernels)
+  const int64_t per_sm = ctas_per_sm > 0 ? ctas_per_sm : 16;
+  const int64_t grid = work < (int64_t)sms * per_sm ? work : (int64_t)sms * per_sm;
   if (vec) k_blend_default<true><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
   else k_blend_default<false><<<(unsigned)grid, kBlendThreads, 0, st>>>(dist_q, ld_dist, col0, (int)Qs, (int)G, lambda_value, row_max_q, final_dist, ld_final, src_rows);
   MPREID_CUDA_CHECK(cudaGetLastError());
@@ -1111,7 +1113,7 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
   // :84-99  dense default, then the sparse accumulation over the touched entries
   const int64_t G = N - Q;
   if (stages & 4) {
-    const int rc = launch_blend_default(dist_q, ld_dist, col0, rows_global ? q_ids : nullptr, row_max_q, Qs, G, lambda_value, final_dist, ld_final, st);
+    const int rc = launch_blend_default(dist_q, ld_dist, col0, rows_global ? q_ids : nullptr, row_max_q, Qs, G, lambda_value, final_dist, ld_final, 0, st);
     if (rc != MPREID_OK) return rc;
   }
   if (!(stages & 2)) return MPREID_OK;
@@ -1167,10 +1169,11 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
 
 // The dense default blend alone (stage 4 of mpreid_rerank_finish_ex without any of the sparse-stage arguments).
 extern "C" int mpreid_rerank_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
-                                           int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, void* stream) {
+                                           int64_t Qs, int64_t G, float lambda_value, float* final_dist, int64_t ld_final, int ctas_per_sm,
+                                           void* stream) {
   MPREID_REQUIRE(dist_q && row_max_q && final_dist && Qs > 0 && G > 0 && col0 >= 0 && ld_dist >= col0 + G && ld_final >= G && Qs < INT32_MAX && G < INT32_MAX,
                  "rerank_blend_default: bad arguments");
-  return launch_blend_default(dist_q, ld_dist, col0, src_rows, row_max_q, Qs, G, lambda_value, final_dist, ld_final, (cudaStream_t)stream);
+  return launch_blend_default(dist_q, ld_dist, col0, src_rows, row_max_q, Qs, G, lambda_value, final_dist, ld_final, ctas_per_sm, (cudaStream_t)stream);
 }
 
 // General form: gallery sample 0 sits at column col0 of dist_q (col0 = Q for rows of the all-pairs matrix, 0 or the

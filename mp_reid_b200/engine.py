@@ -536,7 +536,7 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
 
 
 def rerank_blend_default(dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor, N: int, Q: int, lambda_value: float,
-                         out: torch.Tensor, block_col0: int | None = None, rows_global: bool = False):
+                         out: torch.Tensor, block_col0: int | None = None, rows_global: bool = False, ctas_per_sm: int = 0):
     """The dense part of utils/reranking.py:95 (Jaccard distance 1 wherever the query shares no V column with the gallery
     sample): depends only on the distance block and the maxima, so it can run on a side stream while the sparse stages run."""
     lib = L.load()
@@ -544,5 +544,5 @@ def rerank_blend_default(dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, r
     col0 = Q if block_col0 is None else int(block_col0)
     with torch.cuda.device(out.device):
         L.check(lib.mpreid_rerank_blend_default(dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids) if rows_global else None,
-                                                row_max_q.data_ptr(), Qs, N - Q, float(lambda_value), out.data_ptr(), out.stride(0), _stream()),
-                "rerank_blend_default")
+                                                row_max_q.data_ptr(), Qs, N - Q, float(lambda_value), out.data_ptr(), out.stride(0),
+                                                int(ctas_per_sm), _stream()), "rerank_blend_default")

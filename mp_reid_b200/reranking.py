@@ -27,17 +27,6 @@ def _all_pairs(prep: E.Prepared, precision=None, row_max: torch.Tensor | None = 
     return E.dist_matrix_all_pairs(prep, precision, out=buf, row_max=row_max)
 
 
-_SIDE = {}
-
-
-def _side_stream(dev):
-    """One long-lived auxiliary stream per device (a fresh stream per call would get a fresh allocator pool)."""
-    key = (dev.type, dev.index)
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
-    return _SIDE[key]
-
-
 FUSED_MIN_N = 8192        # below this the all-pairs matrix is a few hundred MB and the plain path is as fast
 FUSED_SAMPLE = 2048       # columns sampled for the per-row thresholds
 
@@ -77,23 +66,14 @@ def _rerank_fused(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_val
     cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))
     cand, cnt, block, col0, row_max = E.dist_symmetric_topk(prep, thr, cap, query_num, precision)
     E.mark("rerank.all_pairs_gemm")
-    # the dense default blend (8 bytes per (query, gallery) pair, HBM bound) needs only the block and the maxima: it runs
-    # on a side stream underneath the latency-bound sparse stages (top-K, V0, query expansion, inverted index)
-    final = E.alloc_dist(query_num, N - query_num, dev)
-    main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        E.rerank_blend_default(block, None, row_max[:query_num], N, query_num, lambda_value, final, block_col0=col0)
     nbr, nbr_val, status = E.cand_topk(cand, cnt, K, row_max, thr)
     E.mark("rerank.topk")
     del cand
     v0 = E.rerank_build_v0_sparse(None, N, N, k1, nbr, nbr_val, row_max, prep.xn, prep.sqnorm)
     E.mark("rerank.v0")
-    ws = E.rerank_finish_workspace(N, query_num, k1, k2, dev)   # both calls work on the same V / inverted-index arrays
-    E.rerank_finish(nbr, v0, block, None, row_max[:query_num], N, query_num, k1, k2, lambda_value, out=final, block_col0=col0, stages=1, ws=ws)
-    main.wait_stream(side)
-    E.rerank_finish(nbr, v0, block, None, row_max[:query_num], N, query_num, k1, k2, lambda_value, out=final, block_col0=col0, stages=2, ws=ws)
+    # (running the dense default blend on a side stream underneath these latency-bound stages was measured: the streaming
+    #  kernel doubles the duration of the gather-bound V0 kernel, whatever its footprint; net gain zero, so it stays in line)
+    final = E.rerank_finish(nbr, v0, block, None, row_max[:query_num], N, query_num, k1, k2, lambda_value, block_col0=col0)
     return final, status
 
 
