@@ -312,6 +312,43 @@ def _metrics():
     return metrics
 
 
+# Peer-to-peer exchange of the gallery slices (NCCL runs only): every rank publishes its uploaded slice in a symmetric-memory
+# buffer (torch.distributed._symmetric_memory: the same allocation mapped into every process of the node) and PULLS the other
+# slices with plain device-to-device copies, which the copy engines move over NVLink -- no SM is taken from the persistent
+# distance GEMM, unlike the NCCL broadcast kernels.  MPREID_SHARD_EXCHANGE=nccl keeps the broadcasts.
+_SYMM = {}
+
+
+def _symm_slice_buffer(rows: int, D: int, dev, group):
+    """-> dict(buf [cap, D] fp32 symmetric, hdl, rows=cap) with cap >= rows, or None (every rank takes the same answer)."""
+    if os.environ.get("MPREID_SHARD_EXCHANGE", "p2p").lower() != "p2p" or not _is_nccl(group):
+        return None
+    key = (id(group), int(D), dev.index)
+    ent = _SYMM.get(key)
+    if ent is False:
+        return None
+    if ent is not None and ent["rows"] >= rows:
+        return ent
+    ok, new = 1.0, None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        cap = (int(rows) + 31) // 32 * 32
+        buf = symm.empty((cap, D), dtype=torch.float32, device=dev)
+        hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        new = dict(buf=buf, hdl=hdl, rows=cap)
+    except Exception as e:   # no P2P mapping on this box / build: fall back for good
+        ok = 0.0
+        if dist.get_rank(group) == 0:
+            print(f"[mp_reid_b200] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL broadcasts", flush=True)
+    flag = torch.tensor([ok], dtype=torch.float32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks or none
+    if float(flag.item()) < 1.0:
+        _SYMM[key] = False
+        return None
+    _SYMM[key] = new
+    return new
+
+
 def sharded_evaluator(num_query_local: int, **kw):
     """R1_mAP_eval whose compute() is cooperative over the ranks of `group` (keyword, default WORLD): update() takes
     this rank's query batches followed by this rank's gallery batches.  See R1_mAP_eval_sharded.compute."""
@@ -395,10 +432,27 @@ def _make_sharded_class():
             copied, next_piece = 0, 0
             n_sub = [(c + sub - 1) // sub for c in g_counts]
             stages = max(n_sub + [0])
+            symm = _symm_slice_buffer(S, D, dev, group) if world > 1 else None
 
-            def exchange(j):
-                """Enqueue (side stream) the broadcasts of sub-block j of every slice -> [(lo, hi, work)]."""
+            def land_own(j):
+                """(side stream) this rank's rows of sub-block j: wait for their upload pieces, move them into place."""
                 nonlocal copied, next_piece
+                lo = int(offs[rank]) + j * sub
+                hi = min(int(offs[rank + 1]), lo + sub)
+                need = hi - int(offs[rank])   # own rows that must have landed
+                while copied < need:
+                    bi, t = g_parts[next_piece]
+                    ev = self._events[bi]
+                    if ev is not None:
+                        xs.wait_event(ev)
+                    else:
+                        xs.wait_stream(main)
+                    gfull[int(offs[rank]) + copied: int(offs[rank]) + copied + t.shape[0]].copy_(t, non_blocking=True)
+                    copied += t.shape[0]; next_piece += 1
+                return lo, hi
+
+            def exchange_nccl(j):
+                """Enqueue (side stream) the broadcasts of sub-block j of every slice -> [(lo, hi, work)]."""
                 out = []
                 with torch.cuda.stream(xs):
                     for r in range(world):
@@ -407,19 +461,35 @@ def _make_sharded_class():
                         lo = int(offs[r]) + j * sub
                         hi = min(int(offs[r + 1]), lo + sub)
                         if r == rank:
-                            need = hi - int(offs[r])   # own rows that must have landed
-                            while copied < need:
-                                bi, t = g_parts[next_piece]
-                                ev = self._events[bi]
-                                if ev is not None:
-                                    xs.wait_event(ev)
-                                else:
-                                    xs.wait_stream(main)
-                                gfull[int(offs[r]) + copied: int(offs[r]) + copied + t.shape[0]].copy_(t, non_blocking=True)
-                                copied += t.shape[0]; next_piece += 1
+                            land_own(j)
                         src = dist.get_global_rank(group, r) if group is not None else r
                         out.append((lo, hi, broadcast(gfull[lo:hi], src, group, async_op=True)))
                 return out
+
+            def exchange_p2p(j):
+                """Sub-block j of every slice by copy engine: publish the own rows in the symmetric buffer, one signal-pad
+                barrier (a one-warp kernel, no shared memory: it fits next to the GEMM CTAs), then pull the peers' rows."""
+                out = []
+                hdl, sbuf = symm["hdl"], symm["buf"]
+                with torch.cuda.stream(xs):
+                    if j < n_sub[rank]:
+                        lo, hi = land_own(j)
+                        sbuf[j * sub: j * sub + (hi - lo)].copy_(gfull[lo:hi], non_blocking=True)
+                        ev = torch.cuda.Event(); ev.record(xs)
+                        out.append((lo, hi, _StreamWork(ev)))     # the own rows do not wait for anybody
+                    hdl.barrier(channel=0)                        # every rank has published its sub-block j
+                    for r in range(world):
+                        if r == rank or j >= n_sub[r]:
+                            continue
+                        lo = int(offs[r]) + j * sub
+                        hi = min(int(offs[r + 1]), lo + sub)
+                        peer = hdl.get_buffer(r, (symm["rows"], D), torch.float32)
+                        gfull[lo:hi].copy_(peer[j * sub: j * sub + (hi - lo)], non_blocking=True)
+                        ev = torch.cuda.Event(); ev.record(xs)
+                        out.append((lo, hi, _StreamWork(ev)))
+                return out
+
+            exchange = exchange_p2p if symm is not None else exchange_nccl
 
             # queries of this rank
             self._wait(0, (q_parts[-1][0] + 1) if q_parts else 0)
