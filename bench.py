@@ -272,7 +272,7 @@ def run_ours(args, data, workload, wkey):
     batch = 8192
     dist_buf = E.alloc_dist(Q, G, dev)
     launches = [0]
-    n_slots = args.steps
+    n_slots = max(args.steps, args.warmup)
     # per-step result slots: the packed per-query buffer of every timed step.  N = 1: copied to a pinned host slot as
     # soon as the step's kernels are queued and reduced by numpy one step later (while the GPU runs the next step).
     # N > 1: the slots stay on the device and travel with ONE all-gather after the last step -- no collective and no
@@ -399,8 +399,7 @@ def run_ours(args, data, workload, wkey):
 
     # ---- `value`: W warm-up steps, then exactly K timed steps
     def warm():
-        for _ in range(args.warmup):
-            step_kernels(None)
+        run_steps(args.warmup)      # the same code path as the timed steps (first use of a collective shape costs milliseconds)
         torch.cuda.synchronize()
     ms_total, results, clocks = timed_region(lambda: run_steps(args.steps), warm, sample_clocks=True)
     n_launch = launches[0] - (2 + E.RANK_EVAL_LAUNCHES) * args.warmup
