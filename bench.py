@@ -312,9 +312,12 @@ def run_ours(args, data, workload, wkey):
                 copy_done[slot].record()
         return res
 
+    t_begin = [0.0]
+
     def run_steps(steps):
         """`steps` passes; returns the (cmc, mAP) of every pass (rank 0; None elsewhere)."""
         results = []
+        t_begin[0] = time.perf_counter()
         for s in range(steps):
             step_kernels(s)
             if not distributed and s > 0:           # reduce the previous step while this one runs
@@ -324,6 +327,9 @@ def run_ours(args, data, workload, wkey):
             copy_done[steps - 1].synchronize()
             results.append(reduce_host([unpack(host_slots[steps - 1].numpy(), Q)]))
             return results
+        t_loop = time.perf_counter()
+        if os.environ.get("MPREID_BENCH_DEBUG"):
+            torch.cuda.synchronize(); t_sync = time.perf_counter()
         out = torch.empty((world, steps, slot_bytes), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(out.view(-1), dev_slots[:steps].reshape(-1))
         # every rank now holds every step's per-query results: the host reductions (numpy, global query order) are dealt out
@@ -339,8 +345,12 @@ def run_ours(args, data, workload, wkey):
                 cmc, mAP = reduce_host([unpack(h[r, k], counts[r]) for r in range(world)])
                 vals[k, : len(cmc)] = cmc; vals[k, 50] = mAP
             res[mine] = torch.from_numpy(vals).to(dev)
+        t_red = time.perf_counter()
         dist.all_reduce(res)
         rh = res.cpu().numpy()
+        if os.environ.get("MPREID_BENCH_DEBUG"):
+            print(f"[bench rank {rank}] steps queued {1e3 * (t_loop - t_begin[0]):.2f} ms, own GPU done +{1e3 * (t_sync - t_loop):.2f}, gather + D2H + "
+                  f"{len(mine)} reductions +{1e3 * (t_red - t_sync):.2f}, all-reduce + D2H +{1e3 * (time.perf_counter() - t_red):.2f}", file=sys.stderr, flush=True)
         return [(rh[s, :50].astype(np.float32), np.float64(rh[s, 50])) for s in range(steps)]
 
     # ---- e2e inputs

@@ -46,8 +46,9 @@ for junk in ("none", "pid_cam"):
 # ---- row-sharded re-ranking: this rank's query rows of final_dist == the same rows of the one-GPU result
 dev = torch.device("cuda", local)
 centers = rng.randn(40, 96).astype(np.float32)
-lab = rng.randint(0, 40, 2300)
-feats = torch.from_numpy(centers[lab] + 1.3 * rng.randn(2300, 96).astype(np.float32)).to(dev)
+NS = 2301          # odd: the row shards are ragged
+lab = rng.randint(0, 40, NS)
+feats = torch.from_numpy(centers[lab] + 1.3 * rng.randn(NS, 96).astype(np.float32)).to(dev)
 nq = 301
 prep = E.prep_rows(feats, normalize=True, keep_xn=True)   # the fused pipelines read feature rows
 for fused in ("1", "0"):          # the fused (no N x N matrix) pipeline and the materialising one
@@ -63,10 +64,14 @@ for fused in ("1", "0"):          # the fused (no N x N matrix) pipeline and the
         assert torch.equal(got, want[ids]), (rank, fused, k1, k2, float((got - want[ids]).abs().max()))
         # per-query results gathered into global query order == one-GPU evaluation of the whole matrix
         q_pid = torch.from_numpy(lab[:nq]).to(dev); g_pid = torch.from_numpy(lab[nq:]).to(dev)
-        fh, ap, nr = E.rank_eval(got, q_pid[ids], g_pid)
-        cmc, mAP = MD.sharded_reduce(fh, ap, nr, None, 50, 2300 - nq, ids=ids, total=nq)
+        if ids.numel():
+            fh, ap, nr = E.rank_eval(got, q_pid[ids], g_pid)
+        else:   # more ranks than 256-row query blocks: this rank finishes no query row
+            fh, ap, nr = (torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
+                          torch.zeros(0, dtype=torch.int32, device=dev))
+        cmc, mAP = MD.sharded_reduce(fh, ap, nr, None, 50, NS - nq, ids=ids, total=nq)
         fh0, ap0, nr0 = E.rank_eval(want, q_pid, g_pid)
-        cmc0, mAP0 = E.reduce_cmc_map(fh0.cpu().numpy(), ap0.cpu().numpy(), nr0.cpu().numpy(), 50, 2300 - nq)
+        cmc0, mAP0 = E.reduce_cmc_map(fh0.cpu().numpy(), ap0.cpu().numpy(), nr0.cpu().numpy(), 50, NS - nq)
         assert mAP == mAP0 and np.array_equal(cmc, cmc0)
 os.environ.pop("MPREID_RERANK_FUSED")
 # ---- the C-ABI communicator (mpreid_comm_*): the three collectives of the path between the ranks, without torch.distributed
