@@ -189,6 +189,9 @@ MPREID_API int mpreid_eval_features(const float* qf, int64_t ld_q, const float* 
 MPREID_API int mpreid_row_topk(const float* dist, int64_t ld_dist, int64_t Q, int64_t G, int k,
                     const float* row_scale, int32_t* idx, float* val, void* stream);
 MPREID_API int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int64_t G, float* row_max, void* stream);
+/* out[r] = the t-th smallest value (1-based, numpy sort order) of row r of a short-row matrix [R, S], S <= 4096: the
+ * per-row thresholds of the fused all-pairs pass (np.partition(row, t-1)[t-1]).                                      */
+MPREID_API int mpreid_row_kth(const float* dist, int64_t ld_dist, int64_t R, int64_t S, int t, float* out, void* stream);
 
 /* ---- k-reciprocal re-ranking (utils/reranking.py:29-100) --------------------------------------
  * `dist` is the all-pairs matrix in the orientation dist[i][j] = reference distmat[j][i] (:46

@@ -382,6 +382,35 @@ k_merge_topk(const unsigned long long* __restrict__ keys_all, int P, int N, int 
   }
 }
 
+// t-th smallest value (1-based) of every row of a SHORT-row matrix [R, S], S <= 32 * PER: the per-row thresholds of the
+// fused all-pairs pass (distances to 2,048 sampled columns).  One warp per row, the row's sort keys in registers, the
+// answer found bit by bit (the largest prefix with fewer than t keys below it): 32 rounds of PER compares and one warp sum.
+template <int PER>
+__global__ void __launch_bounds__(256)
+k_row_kth(const float* __restrict__ m, int64_t ld, int R, int S, int t, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < R; row += gridDim.x * 8) {
+    const float* r = m + (int64_t)row * ld;
+    uint32_t key[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      key[j] = c < S ? order_key(__ldg(r + c)) : 0xffffffffu;
+    }
+    uint32_t ans = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t trial = ans | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) c += key[j] < trial ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c < t) ans = trial;
+    }
+    if (lane == 0) out[row] = order_key_inv(ans);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_row_max(const float* __restrict__ dist, int64_t ld, int Q, int G, float* __restrict__ row_max) {
   __shared__ float sh[8];
@@ -479,6 +508,20 @@ extern "C" int mpreid_merge_topk(const uint64_t* keys_all, int P, int64_t N, int
   const int64_t want = ceil_div(N, 4);
   const int64_t grid = want < (int64_t)sms * 6 ? want : (int64_t)sms * 6;
   k_merge_topk<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const unsigned long long*)keys_all, P, (int)N, k, row_scale, thr, idx, val, status);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+extern "C" int mpreid_row_kth(const float* dist, int64_t ld_dist, int64_t R, int64_t S, int t, float* out, void* stream) {
+  MPREID_REQUIRE(dist && out && R > 0 && S > 0 && ld_dist >= S && R < INT32_MAX, "row_kth: bad arguments");
+  MPREID_REQUIRE(S <= 4096 && t >= 1 && t <= S, "row_kth: needs S <= 4096 and 1 <= t <= S (got S=%lld t=%d)", (long long)S, t);
+  const int sms = sm_count_of_current_device();
+  const int64_t want = ceil_div(R, 8);
+  const int64_t grid = want < (int64_t)sms * 8 ? want : (int64_t)sms * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S <= 512) k_row_kth<16><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  else if (S <= 2048) k_row_kth<64><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  else k_row_kth<128><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

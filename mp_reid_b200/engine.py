@@ -341,6 +341,17 @@ def row_topk(dist: torch.Tensor, k: int, row_scale: torch.Tensor | None = None, 
     return (idx, val) if want_values else idx
 
 
+def row_kth(dist: torch.Tensor, t: int) -> torch.Tensor:
+    """The t-th smallest value (1-based) of every row of a short-row matrix (at most 4,096 columns)."""
+    require_cuda()
+    lib = L.load()
+    R, S = dist.shape
+    out = torch.empty((R,), dtype=torch.float32, device=dist.device)
+    with torch.cuda.device(dist.device):
+        L.check(lib.mpreid_row_kth(dist.data_ptr(), dist.stride(0), R, S, int(t), out.data_ptr(), _stream()), "row_kth")
+    return out
+
+
 def row_max(dist: torch.Tensor) -> torch.Tensor:
     require_cuda()
     lib = L.load()

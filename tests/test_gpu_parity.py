@@ -1149,3 +1149,18 @@ def test_comm_c_abi_single_rank():
     assert torch.equal(x, torch.arange(1000, dtype=torch.float32, device=DEV)) and torch.equal(x, y)
     L.check(lib.mpreid_comm_destroy(comm), "comm_destroy")
     assert lib.mpreid_comm_broadcast(None, x.data_ptr(), 4, 0, st) != 0      # null communicator -> error code, no crash
+
+
+def test_row_kth_equals_numpy_partition():
+    """mpreid_row_kth (thresholds of the fused all-pairs pass): t-th smallest per row in numpy's sort order, with ties,
+    negative zero, infinities and NaN (sorted last), row widths on both sides of the register-tile sizes."""
+    rs = np.random.RandomState(13)
+    for (R, S, t) in [(37, 600, 23), (200, 2048, 23), (50, 2048, 1), (9, 2048, 2048), (33, 31, 7), (20, 3000, 100), (5, 512, 512)]:
+        a = rs.randn(R, S).astype(np.float32)
+        a[:, ::7] = np.round(a[:, ::7], 1)               # ties
+        a[0, :5] = [-0.0, 0.0, np.inf, -np.inf, np.nan]
+        if R > 3:
+            a[3, : S // 2] = np.nan
+        got = E.row_kth(dev(a), t).cpu().numpy()
+        want = np.sort(a, axis=1)[:, t - 1]              # numpy sorts NaN last
+        assert np.array_equal(got, want, equal_nan=True), (R, S, t)
