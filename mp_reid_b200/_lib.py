@@ -41,6 +41,7 @@ SIGNATURES = {
     "mpreid_row_topk": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
     "mpreid_row_max": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "mpreid_row_kth": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
+    "mpreid_row_kth_bound": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "mpreid_rerank_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mpreid_rerank": (_i32, [_p, _i64, _p, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _p, _p]),
     "mpreid_rerank_neighbor_count": (_i32, [_i32, _i32]),

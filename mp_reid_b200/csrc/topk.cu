@@ -411,6 +411,48 @@ k_row_kth(const float* __restrict__ m, int64_t ld, int R, int S, int t, float* _
   }
 }
 
+// A cheap UPPER BOUND of the t-th smallest value of every row (what the fused all-pairs pass needs from the sampled
+// columns: any threshold that at least t elements of the row stay below is valid; a looser one only lengthens the
+// candidate lists).  Every lane keeps the M smallest of its strided share of the row (three min/max per element), then
+// the warp pops the t smallest of those 32 * M values: the result is the t-th smallest of a SUBSET of the row, hence
+// >= the row's t-th smallest, and equal to it unless some lane held more than M of the row's t smallest values.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_row_kth_bound(const float* __restrict__ m, int64_t ld, int R, int S, int t, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < R; row += gridDim.x * 8) {
+    const float* r = m + (int64_t)row * ld;
+    float a[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) a[i] = INFINITY;
+    for (int c0 = 0; c0 < S; c0 += 128) {           // four independent loads per lane and trip
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int c = c0 + u * 32 + lane; v[u] = c < S ? __ldg(r + c) : INFINITY; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x = v[u] == v[u] ? v[u] : INFINITY;   // NaN sorts last
+#pragma unroll
+        for (int i = 0; i < M; ++i) { const float hi = fmaxf(a[i], x); a[i] = fminf(a[i], x); x = hi; }   // insertion into the sorted M
+      }
+    }
+    float kth = INFINITY;
+    for (int round = 0; round < t; ++round) {       // pop the minimum of the 32 lane heads t times
+      float mn = a[0];
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      kth = mn;
+      const unsigned who = __ballot_sync(0xffffffffu, a[0] == mn);
+      if (who == 0u) break;                         // (only NaN / empty left)
+      if (lane == __ffs(who) - 1) {
+#pragma unroll
+        for (int i = 0; i + 1 < M; ++i) a[i] = a[i + 1];
+        a[M - 1] = INFINITY;
+      }
+    }
+    if (lane == 0) out[row] = kth;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_row_max(const float* __restrict__ dist, int64_t ld, int Q, int G, float* __restrict__ row_max) {
   __shared__ float sh[8];
@@ -522,6 +564,19 @@ extern "C" int mpreid_row_kth(const float* dist, int64_t ld_dist, int64_t R, int
   if (S <= 512) k_row_kth<16><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
   else if (S <= 2048) k_row_kth<64><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
   else k_row_kth<128><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  MPREID_CUDA_CHECK(cudaGetLastError());
+  return MPREID_OK;
+}
+
+extern "C" int mpreid_row_kth_bound(const float* dist, int64_t ld_dist, int64_t R, int64_t S, int t, float* out, void* stream) {
+  MPREID_REQUIRE(dist && out && R > 0 && S > 0 && ld_dist >= S && R < INT32_MAX, "row_kth_bound: bad arguments");
+  MPREID_REQUIRE(t >= 1 && t <= 128 && t <= S, "row_kth_bound: needs 1 <= t <= min(128, S) (got S=%lld t=%d)", (long long)S, t);
+  const int sms = sm_count_of_current_device();
+  const int64_t want = ceil_div(R, 8);
+  const int64_t grid = want < (int64_t)sms * 8 ? want : (int64_t)sms * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t <= 64) k_row_kth_bound<2><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  else k_row_kth_bound<4><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

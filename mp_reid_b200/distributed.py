@@ -202,7 +202,7 @@ def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, 
     ids = (torch.arange(S, device=dev, dtype=torch.int64) * N) // S
     smp = prep_all.take(ids)
     dS = E.dist_matrix(prep_all.rows(lo, hi), smp, "sqeuclid", precision)
-    thr = _allgather_contig(E.row_kth(dS, t) + 1e-6 * (prep_all.sqnorm[lo:hi] + prep_all.sqnorm.max()), counts, group)
+    thr = _allgather_contig(E.row_kth(dS, t, bound=True) + 1e-6 * (prep_all.sqnorm[lo:hi] + prep_all.sqnorm.max()), counts, group)
     E.mark("rerank.thresholds")
     expect = N * t / S
     cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))

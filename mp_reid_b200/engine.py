@@ -341,14 +341,16 @@ def row_topk(dist: torch.Tensor, k: int, row_scale: torch.Tensor | None = None, 
     return (idx, val) if want_values else idx
 
 
-def row_kth(dist: torch.Tensor, t: int) -> torch.Tensor:
-    """The t-th smallest value (1-based) of every row of a short-row matrix (at most 4,096 columns)."""
+def row_kth(dist: torch.Tensor, t: int, bound: bool = False) -> torch.Tensor:
+    """The t-th smallest value (1-based) of every row of a short-row matrix (at most 4,096 columns); bound=True (t <= 128):
+    a cheap upper bound of it instead (the t-th smallest of a subset of the row) -- all a threshold needs."""
     require_cuda()
     lib = L.load()
     R, S = dist.shape
     out = torch.empty((R,), dtype=torch.float32, device=dist.device)
+    fn = lib.mpreid_row_kth_bound if (bound and t <= 128) else lib.mpreid_row_kth
     with torch.cuda.device(dist.device):
-        L.check(lib.mpreid_row_kth(dist.data_ptr(), dist.stride(0), R, S, int(t), out.data_ptr(), _stream()), "row_kth")
+        L.check(fn(dist.data_ptr(), dist.stride(0), R, S, int(t), out.data_ptr(), _stream()), "row_kth")
     return out
 
 

@@ -59,7 +59,7 @@ def _rerank_fused(prep: E.Prepared, query_num: int, k1: int, k2: int, lambda_val
     ids = (torch.arange(S, device=dev, dtype=torch.int64) * N) // S
     smp = prep.take(ids)
     dS = E.dist_matrix(prep, smp, "sqeuclid", precision)
-    thr = E.row_kth(dS, t) + 1e-6 * (prep.sqnorm + prep.sqnorm.max())
+    thr = E.row_kth(dS, t, bound=True) + 1e-6 * (prep.sqnorm + prep.sqnorm.max())
     E.mark("rerank.thresholds")
     expect = N * t / S
     cap = int(min(N, max(256, (int(3 * expect) + 256 + 255) // 256 * 256)))

@@ -1164,3 +1164,17 @@ def test_row_kth_equals_numpy_partition():
         got = E.row_kth(dev(a), t).cpu().numpy()
         want = np.sort(a, axis=1)[:, t - 1]              # numpy sorts NaN last
         assert np.array_equal(got, want, equal_nan=True), (R, S, t)
+
+
+def test_row_kth_bound_is_a_valid_tight_threshold():
+    """mpreid_row_kth_bound: never below the exact t-th smallest, the t-th smallest of a subset of the row (so at least t
+    row elements stay <= it), and equal to the exact value for nearly every row of a random matrix."""
+    rs = np.random.RandomState(14)
+    for (R, S, t) in [(300, 2048, 23), (100, 2048, 53), (64, 600, 23), (40, 2048, 103), (10, 40, 23)]:
+        a = rs.randn(R, S).astype(np.float32)
+        a[0, :4] = [np.nan, np.inf, -np.inf, -0.0]
+        exact = np.sort(a, axis=1)[:, t - 1]
+        got = E.row_kth(dev(a), t, bound=True).cpu().numpy()
+        assert (got >= exact).all()
+        assert ((a <= got[:, None]).sum(1) >= t).all()
+        assert (got == exact).mean() >= 0.5 and np.isin(got, a).all()
