@@ -192,8 +192,8 @@ MPREID_API int mpreid_row_max(const float* dist, int64_t ld_dist, int64_t Q, int
 /* out[r] = the t-th smallest value (1-based, numpy sort order) of row r of a short-row matrix [R, S], S <= 4096: the
  * per-row thresholds of the fused all-pairs pass (np.partition(row, t-1)[t-1]).                                      */
 MPREID_API int mpreid_row_kth(const float* dist, int64_t ld_dist, int64_t R, int64_t S, int t, float* out, void* stream);
-/* A cheap upper bound of the same (t <= 128): the t-th smallest of a subset of the row (every lane of a warp keeps the 2 or
- * 4 smallest of its strided share), i.e. >= the exact value and usually equal to it.  What the thresholds need: at least
+/* A cheap upper bound of the same (t <= 128): the t-th smallest of a subset of the row (every lane of a warp keeps the 4 to
+ * 16 smallest of its strided share), i.e. >= the exact value and usually equal to it.  What the thresholds need: at least
  * t elements of the row are <= out[r].                                                                               */
 MPREID_API int mpreid_row_kth_bound(const float* dist, int64_t ld_dist, int64_t R, int64_t S, int t, float* out, void* stream);
 

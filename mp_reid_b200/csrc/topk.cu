@@ -575,8 +575,11 @@ extern "C" int mpreid_row_kth_bound(const float* dist, int64_t ld_dist, int64_t 
   const int64_t want = ceil_div(R, 8);
   const int64_t grid = want < (int64_t)sms * 8 ? want : (int64_t)sms * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (t <= 64) k_row_kth_bound<2><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
-  else k_row_kth_bound<4><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  // M per lane: the row's t smallest land ~t/32 per lane (Poisson); M is chosen so that a lane holds more than M of them
+  // in well under 1 % of the rows (then the bound is exact)
+  if (t <= 32) k_row_kth_bound<4><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  else if (t <= 64) k_row_kth_bound<8><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
+  else k_row_kth_bound<16><<<(unsigned)grid, 256, 0, st>>>(dist, ld_dist, (int)R, (int)S, t, out);
   MPREID_CUDA_CHECK(cudaGetLastError());
   return MPREID_OK;
 }

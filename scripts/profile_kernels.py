@@ -22,7 +22,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 sub = torch.cat([feats[:3368], feats[Q:Q + 15913]])
 for _ in range(2):
-    ps = E.prep_rows(sub, True, prec, keep_xn=False)
+    ps = E.prep_rows(sub, True, prec, keep_xn=True)
     out = _rerank_device(ps, 3368, 20, 6, 0.3, prec)
 torch.cuda.synchronize()
 print("done", float(ap.sum()), float(out.sum()))
