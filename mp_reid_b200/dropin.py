@@ -7,6 +7,10 @@ processor/processor_uniprompt_stage2.py:7) and ``from utils.reranking import re_
 (utils/metrics.py:4).  Its ``utils`` package also holds logger / meter / iotools, so the package is
 NOT shadowed: only the two module names are pre-seeded in ``sys.modules`` and everything else keeps
 loading from the reference tree.
+
+``MPREID_DROPIN_LOSSES=1`` additionally serves the two training-side distance workloads of SURVEY 8f:
+``loss.triplet_loss`` (TripletLoss, loss/make_loss.py:7) and ``loss.supcontrast`` (SupConLoss,
+processor/processor_uniprompt_stage1.py:9) resolve to mp_reid_b200.triplet / mp_reid_b200.supcon.
 """
 from __future__ import annotations
 
@@ -23,6 +27,10 @@ def install() -> None:
     if pkg is not None:
         pkg.metrics = metrics
         pkg.reranking = reranking
+    if os.environ.get("MPREID_DROPIN_LOSSES", "0") == "1":
+        from . import supcon, triplet
+        sys.modules["loss.triplet_loss"] = triplet
+        sys.modules["loss.supcontrast"] = supcon
 
 
 def main(argv=None) -> None:

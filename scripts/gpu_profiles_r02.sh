@@ -25,4 +25,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_di
    python scripts/rerank_stages.py msmt17 1 > gpurun_out/r02_ncu_fused_msmt17.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_jaccard_bucket -s 1 -c 1 -f -o gpurun_out/r02_prof_k_jaccard_bucket_msmt17 \
    python scripts/rerank_stages.py msmt17 1 >> gpurun_out/r02_ncu_fused_msmt17.log 2>&1
+# summarise on the box (the reports with imported source are ~20 MB each; only gpurun_out/ <= 64 MiB travels back)
+python scripts/collect_profiles_r02.py gpurun_out/profiles_r02 > gpurun_out/r02_traffic.log 2>&1
+find gpurun_out -name "r02_prof_*.ncu-rep" -size +6M -delete
 ls -la gpurun_out/r02_prof_*.ncu-rep | wc -l

@@ -85,6 +85,24 @@ def test_dropin_seeds_only_the_two_hot_path_modules(tmp_path):
     assert "META mp_reid_b200.metrics utils.meter mp_reid_b200.metrics mp_reid_b200.reranking" in out.stdout
 
 
+def test_dropin_can_also_serve_the_loss_modules(tmp_path):
+    """MPREID_DROPIN_LOSSES=1: `from .triplet_loss import TripletLoss` inside the reference's loss package (loss/make_loss.py:7)
+    and `from loss.supcontrast import SupConLoss` (processor/processor_uniprompt_stage1.py:9) resolve to this package."""
+    import subprocess
+    (tmp_path / "loss").mkdir()
+    (tmp_path / "loss" / "__init__.py").write_text("from .make_loss import make_loss\n")
+    (tmp_path / "loss" / "make_loss.py").write_text("from .triplet_loss import TripletLoss\n\ndef make_loss():\n    return TripletLoss(0.3)\n")
+    (tmp_path / "loss" / "triplet_loss.py").write_text("raise RuntimeError('the reference module must not be imported')\n")
+    (tmp_path / "loss" / "supcontrast.py").write_text("raise RuntimeError('the reference module must not be imported')\n")
+    (tmp_path / "script.py").write_text(
+        "from loss import make_loss\nfrom loss.supcontrast import SupConLoss\n"
+        "print('META', type(make_loss()).__module__, make_loss().margin, SupConLoss.__module__)\n")
+    out = subprocess.run([sys.executable, "-m", "mp_reid_b200.dropin", str(tmp_path / "script.py")], cwd=ROOT,
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, MPREID_DROPIN_LOSSES="1"))
+    assert out.returncode == 0, out.stderr
+    assert "META mp_reid_b200.triplet 0.3 mp_reid_b200.supcon" in out.stdout
+
+
 def test_aligned_shard_bounds_cover_and_align():
     from mp_reid_b200.distributed import aligned_shard_bounds
     for n, w in [(82161, 8), (82161, 2), (100, 8), (0, 4), (33, 2), (9003, 2), (15913, 4)]:
