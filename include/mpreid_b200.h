@@ -240,7 +240,9 @@ MPREID_API int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
  * and the parts may run as separate calls on the same workspace: stages is a mask of 1 = query expansion + inverted index
  * (:73-82), 2 = sparse Jaccard accumulation and blend of the touched entries (:84-95), 4 = the dense default blend (:95
  * with temp_min = 0; needs only the distance block and the maxima, so it may run early on another stream; 2 must come
- * after 4); 7 = everything.
+ * after 4); 7 = everything.  Sharded query expansion: 8 = expand only the rows [qe_lo, qe_hi) into the workspace (the caller
+ * all-gathers the other rows into the arrays mpreid_rerank_finish_layout locates), 16 = build the inverted index from a
+ * complete V.
  * v0_stride: row stride of v0_col / v0_val in entries (0 = mpreid_rerank_v0_capacity; a sharded run all-gathers the V0
  * rows trimmed to their longest length).  rows_global != 0: dist_q and row_max_q are addressed by the GLOBAL query index
  * q_ids[il] (the [Q, .] block and the [N] maxima a rank holds in the row-sharded form) instead of the local row il.   */
@@ -248,7 +250,9 @@ MPREID_API int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int3
                             const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                             int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                             float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
-                            int64_t v0_stride, int rows_global, void* stream);
+                            int64_t v0_stride, int rows_global, int64_t qe_lo, int64_t qe_hi, void* stream);
+/* byte offsets of v_col int32 [N, C1], v_val fp16 [N, C1], v_len int32 [N] inside the finish workspace, and C1 (k2 > 1) */
+MPREID_API int mpreid_rerank_finish_layout(int64_t N, int64_t Q, int k1, int k2, int64_t* out4);
 /* Stage 4 alone: final[il, c] = fp16(1 - lambda) + lambda * dist_q[row(il), col0 + c] / row_max_q[row(il)], row(il) =
  * src_rows[il] if given (global addressing) else il.  Needs nothing from the sparse stages.  ctas_per_sm > 0 caps the
  * launch to that many 256-thread CTAs per SM (a background launch next to latency-bound kernels); 0 = full occupancy. */

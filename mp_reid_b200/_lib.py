@@ -53,7 +53,9 @@ SIGNATURES = {
     "mpreid_cand_topk": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "mpreid_merge_topk": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "mpreid_rerank_build_v0_sparse": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
-    "mpreid_rerank_finish_ex": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _i32, _i64, _i32, _p]),
+    "mpreid_rerank_finish_ex": (_i32, [_p, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _sz, _i32, _i64, _i32,
+                                       _i64, _i64, _p]),
+    "mpreid_rerank_finish_layout": (_i32, [_i64, _i64, _i32, _i32, C.POINTER(_i64)]),
     "mpreid_rerank_blend_default": (_i32, [_p, _i64, _i64, _p, _p, _i64, _i64, _f32, _p, _i64, _i32, _p]),
     "mpreid_hard_example_mining": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "mpreid_triplet_forward": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),

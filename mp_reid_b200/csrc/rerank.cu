@@ -303,13 +303,13 @@ __global__ void __launch_bounds__(kQeThreads)
 k_query_expand(int N, int K, int k2, const int32_t* __restrict__ nbr,
                const int32_t* __restrict__ v0_col, const uint16_t* __restrict__ v0_val, const int32_t* __restrict__ v0_len, int C0,
                int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1,
-               uint64_t* __restrict__ scratch, int64_t scratch_P, int skip_upto) {
+               uint64_t* __restrict__ scratch, int64_t scratch_P, int skip_upto, int row_lo) {
   __shared__ uint64_t sbuf[kQeSmemEntries];
   __shared__ int sh[33];
   __shared__ int s_total;
   const int tid = threadIdx.x;
   const float inv_cnt = (float)k2;
-  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+  for (int i = row_lo + blockIdx.x; i < N; i += gridDim.x) {   // rows [row_lo, N)
     // gather (col, m, val) of the k2 neighbour rows; key = col<<32 | m<<16 | fp16 bits
     if (tid == 0) {
       int t = 0;
@@ -380,12 +380,12 @@ static constexpr int kQeWarps = 8;
 __global__ void __launch_bounds__(kQeWarps * 32)
 k_query_expand_warp(int N, int K, int k2, const int32_t* __restrict__ nbr,
                     const int32_t* __restrict__ v0_col, const uint16_t* __restrict__ v0_val, const int32_t* __restrict__ v0_len, int C0,
-                    int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1) {
+                    int32_t* __restrict__ v_col, uint16_t* __restrict__ v_val, int32_t* __restrict__ v_len, int64_t C1, int row_lo) {
   __shared__ uint64_t sbuf[kQeWarps][kQeWarpEntries];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* buf = sbuf[warp];
   const float cnt = (float)k2;
-  for (int i = blockIdx.x * kQeWarps + warp; i < N; i += gridDim.x * kQeWarps) {
+  for (int i = row_lo + blockIdx.x * kQeWarps + warp; i < N; i += gridDim.x * kQeWarps) {   // rows [row_lo, N)
     // lane m (< k2 <= 64: two rows per lane) holds neighbour m and the length of its V0 row
     int32_t r[2]; int len[2];
 #pragma unroll
@@ -1046,6 +1046,18 @@ extern "C" size_t mpreid_rerank_finish_workspace_bytes(int64_t N, int64_t Q, int
   return carve_finish(nullptr, nullptr, N, Q, k1, k2, sm_count_of_current_device());
 }
 
+// Where the expanded V rows live inside the finish workspace (k2 != 1): byte offsets of v_col int32 [N, C1], v_val fp16
+// [N, C1], v_len int32 [N], and C1 -- a sharded run expands its own rows (stage 8) and all-gathers the rest into place.
+extern "C" int mpreid_rerank_finish_layout(int64_t N, int64_t Q, int k1, int k2, int64_t* out4) {
+  MPREID_REQUIRE(out4 && N > 1 && Q > 0 && Q < N && k1 >= 1 && k1 <= kMaxK1 && k2 >= 2 && k2 <= 64, "rerank_finish_layout: bad arguments (k2 must be > 1)");
+  FinishWs w;
+  memset(&w, 0, sizeof(w));
+  char* base = (char*)256;   // any non-null base: only the differences matter
+  carve_finish(&w, base, N, Q, k1, k2, sm_count_of_current_device());
+  out4[0] = (char*)w.v_col - base; out4[1] = (char*)w.v_val - base; out4[2] = (char*)w.v_len - base; out4[3] = w.C1;
+  return MPREID_OK;
+}
+
 namespace mpreid {
 
 static int launch_blend_default(const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* src_rows, const float* row_max_q,
@@ -1067,9 +1079,10 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
                               const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                               int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                               float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages, int64_t v0_stride,
-                              int rows_global, cudaStream_t st) {
+                              int rows_global, int64_t qe_lo, int64_t qe_hi, cudaStream_t st) {
   MPREID_REQUIRE(nbr_all && v0_col && v0_val && v0_len && dist_q && row_max_q && final_dist && workspace, "rerank_finish: null pointer");
-  MPREID_REQUIRE(stages >= 1 && stages <= 7, "rerank_finish: stages is a mask of 1 (expand + index), 2 (sparse Jaccard), 4 (default blend)");
+  MPREID_REQUIRE(stages >= 1 && stages <= 31, "rerank_finish: stages is a mask of 1 (expand + index), 2 (sparse Jaccard), 4 (default blend), 8 (expand rows [qe_lo, qe_hi) only), 16 (index only)");
+  MPREID_REQUIRE(!(stages & 8) || (qe_lo >= 0 && qe_lo <= qe_hi && qe_hi <= N), "rerank_finish: bad query-expansion row range");
   MPREID_REQUIRE(!rows_global || q_ids, "rerank_finish: rows_global needs q_ids");
   MPREID_REQUIRE(N > 1 && Q > 0 && Q < N && Qs > 0 && Qs <= Q && N < INT32_MAX && ld_dist >= col0 + (N - Q) && ld_final >= N - Q,
                  "rerank_finish: bad shape N=%lld Q=%lld Qs=%lld", (long long)N, (long long)Q, (long long)Qs);
@@ -1088,18 +1101,26 @@ static int rerank_finish_impl(const int32_t* nbr_all, int K, const int32_t* v0_c
   if (k2 != 1) { v_col = w.v_col; v_val = w.v_val; v_len = w.v_len; }
   const int v0s = (int)(v0_stride > 0 ? v0_stride : w.C0);   // row stride of the V0 arrays (the capacity, or a trimmed width)
   const int64_t vstride = k2 != 1 ? w.C1 : (int64_t)v0s;      // row stride of V (== V0 when there is no query expansion)
-  if (stages & 1) {
-    // :73-78  (every rank expands all N rows: it is cheap and saves an all-gather of the expanded rows)
+  if (stages & (1 | 8)) {
+    // :73-78  all N rows (stage 1: every rank expands everything), or the rows [qe_lo, qe_hi) only (stage 8: the sharded
+    // form, the expanded rows are then all-gathered by the caller straight into the workspace arrays)
     if (k2 != 1) {
-      // rows whose k2 gathered V0 rows hold <= 512 entries: one warp each; the rest (large k1 / k2): one CTA each
-      const int k2e = k2 < Keff ? k2 : Keff;
-      const int64_t wgrid = ceil_div(N, kQeWarps) < (int64_t)sms * 6 ? ceil_div(N, kQeWarps) : (int64_t)sms * 6;
-      k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
-                                                                   w.v_col, w.v_val, w.v_len, w.C1);
-      const int64_t qe_grid = N < w.qe_grid ? N : w.qe_grid;
-      k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)N, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
-                                                               w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P, kQeWarpEntries);
+      const int64_t r_lo = (stages & 1) ? 0 : qe_lo, r_hi = (stages & 1) ? N : qe_hi;
+      const int64_t n_rows = r_hi - r_lo;
+      if (n_rows > 0) {
+        // rows whose k2 gathered V0 rows hold <= 512 entries: one warp each; the rest (large k1 / k2): one CTA each
+        const int k2e = k2 < Keff ? k2 : Keff;
+        const int64_t wgrid = ceil_div(n_rows, kQeWarps) < (int64_t)sms * 6 ? ceil_div(n_rows, kQeWarps) : (int64_t)sms * 6;
+        k_query_expand_warp<<<(unsigned)wgrid, kQeWarps * 32, 0, st>>>((int)r_hi, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
+                                                                     w.v_col, w.v_val, w.v_len, w.C1, (int)r_lo);
+        const int64_t qe_grid = n_rows < w.qe_grid ? n_rows : w.qe_grid;
+        k_query_expand<<<(unsigned)qe_grid, kQeThreads, 0, st>>>((int)r_hi, K, k2e, nbr_all, v0_col, v0_val, v0_len, v0s,
+                                                                 w.v_col, w.v_val, w.v_len, w.C1, w.qe_scratch, w.qe_P, kQeWarpEntries, (int)r_lo);
+      }
     }
+    MPREID_CUDA_CHECK(cudaGetLastError());
+  }
+  if (stages & (1 | 16)) {
     // :80-82 (gallery rows only: the output keeps columns Q.. only, :99)
     k_zero_i32<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(w.col_cnt, w.col_fill, N);
     const int rows_per_cta = 8;
@@ -1164,7 +1185,7 @@ extern "C" int mpreid_rerank_finish(const int32_t* nbr_all, int K, const int32_t
                                     int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                                     float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, void* stream) {
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_qrows, ld_dist, Q, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, 7, 0, 0, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, 7, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 // The dense default blend alone (stage 4 of mpreid_rerank_finish_ex without any of the sparse-stage arguments).
@@ -1184,10 +1205,10 @@ extern "C" int mpreid_rerank_finish_ex(const int32_t* nbr_all, int K, const int3
                                        const float* dist_q, int64_t ld_dist, int64_t col0, const int32_t* q_ids, const float* row_max_q,
                                        int64_t N, int64_t Q, int64_t Qs, int k1, int k2, float lambda_value,
                                        float* final_dist, int64_t ld_final, void* workspace, size_t workspace_bytes, int stages,
-                                       int64_t v0_stride, int rows_global, void* stream) {
+                                       int64_t v0_stride, int rows_global, int64_t qe_lo, int64_t qe_hi, void* stream) {
   MPREID_REQUIRE(col0 >= 0 && v0_stride >= 0, "rerank_finish_ex: col0 / v0_stride < 0");
   return rerank_finish_impl(nbr_all, K, v0_col, v0_val, v0_len, dist_q, ld_dist, col0, q_ids, row_max_q, N, Q, Qs, k1, k2, lambda_value,
-                            final_dist, ld_final, workspace, workspace_bytes, stages, v0_stride, rows_global, (cudaStream_t)stream);
+                            final_dist, ld_final, workspace, workspace_bytes, stages, v0_stride, rows_global, qe_lo, qe_hi, (cudaStream_t)stream);
 }
 
 // single-GPU convenience: neighbours + V0 rows + finish on the whole matrix

@@ -242,7 +242,27 @@ def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, 
     if q_ids.numel() == 0:
         return torch.empty((0, N - nq), dtype=torch.float32, device=dev), q_ids
     q32 = q_ids.to(torch.int32).contiguous()
-    final = E.rerank_finish(nbr, v0_all, block, q32, row_max, N, nq, k1, k2, lambda_value, block_col0=col0, rows_global=True)
+    if k2 == 1 or os.environ.get("MPREID_SHARD_QE", "1") == "0":
+        final = E.rerank_finish(nbr, v0_all, block, q32, row_max, N, nq, k1, k2, lambda_value, block_col0=col0, rows_global=True)
+        return final, q_ids
+    # query expansion sharded like the V0 rows: expand the rows [lo, hi) into the finish workspace, all-gather the other ranks'
+    # rows (trimmed to the longest one) into place, then inverted index + Jaccard + blend
+    ws = E.rerank_finish_workspace(N, nq, k1, k2, dev)
+    final = E.alloc_dist(int(q_ids.numel()), N - nq, dev)
+    args = (nbr, v0_all, block, q32, row_max, N, nq, k1, k2, lambda_value)
+    E.rerank_finish(*args, out=final, block_col0=col0, rows_global=True, stages=8, ws=ws, qe_rows=(lo, hi))
+    v_col, v_val, v_len = E.rerank_finish_v_views(ws, N, nq, k1, k2)
+    wmax = v_len[lo:hi].max().to(torch.float32).view(1)
+    if _is_nccl(group):
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX, group=group)
+        W1 = int(wmax.item())
+    else:
+        h = wmax.cpu(); dist.all_reduce(h, op=dist.ReduceOp.MAX, group=group); W1 = int(h.item())
+    W1 = min(v_col.shape[1], max(8, (W1 + 7) // 8 * 8))
+    v_col[:, :W1] = _allgather_contig(v_col[lo:hi, :W1].contiguous(), counts, group)
+    v_val[:, :W1] = _allgather_contig(v_val[lo:hi, :W1].contiguous(), counts, group)
+    v_len.copy_(_allgather_contig(v_len[lo:hi].contiguous(), counts, group))
+    E.rerank_finish(*args, out=final, block_col0=col0, rows_global=True, stages=16 | 4 | 2, ws=ws)
     return final, q_ids
 
 

@@ -513,9 +513,22 @@ def rerank_finish_workspace(N: int, Q: int, k1: int, k2: int, device) -> torch.T
     return torch.empty((nbytes,), dtype=torch.uint8, device=device)
 
 
+def rerank_finish_v_views(ws: torch.Tensor, N: int, Q: int, k1: int, k2: int):
+    """Tensor views of the expanded V rows inside a finish workspace -> (v_col int32 [N, C1], v_val fp16 [N, C1], v_len int32 [N])."""
+    import ctypes
+    out = (ctypes.c_int64 * 4)()
+    L.check(L.load().mpreid_rerank_finish_layout(N, Q, k1, k2, out), "rerank_finish_layout")
+    o_col, o_val, o_len, C1 = [int(x) for x in out]
+    v_col = ws[o_col: o_col + N * C1 * 4].view(torch.int32).view(N, C1)
+    v_val = ws[o_val: o_val + N * C1 * 2].view(torch.float16).view(N, C1)
+    v_len = ws[o_len: o_len + N * 4].view(torch.int32)
+    return v_col, v_val, v_len
+
+
 def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: torch.Tensor | None, row_max_q: torch.Tensor,
                   N: int, Q: int, k1: int, k2: int, lambda_value: float, out: torch.Tensor | None = None,
-                  block_col0: int | None = None, rows_global: bool = False, stages: int = 7, ws: torch.Tensor | None = None) -> torch.Tensor:
+                  block_col0: int | None = None, rows_global: bool = False, stages: int = 7, ws: torch.Tensor | None = None,
+                  qe_rows: tuple[int, int] = (0, 0)) -> torch.Tensor:
     """utils/reranking.py:73-99 for the query rows `dist_qrows` [Qs, N] -> final [Qs, N-Q].
     block_col0: `dist_qrows` is instead the [Qs, >= col0 + G] buffer of query-to-gallery distances, gallery sample 0 at
     column block_col0 (what the fused all-pairs pass keeps).  rows_global: dist_qrows / row_max_q are the full [Q, .] block
@@ -535,13 +548,14 @@ def rerank_finish(nbr_all: torch.Tensor, v0, dist_qrows: torch.Tensor, q_ids: to
     assert v0_col.is_contiguous() and v0_val.is_contiguous() and v0_col.shape[0] == N and v0_col.shape == v0_val.shape
     col0 = Q if block_col0 is None else int(block_col0)
     with torch.cuda.device(dev):
-        parts = [stages] if _timeline is None else [p for p in (stages & 1, stages & 6) if p]   # timeline mode: separately timed calls
+        parts = [stages] if _timeline is None else [p for p in (stages & 25, stages & 6) if p]   # timeline mode: separately timed calls
         for part in parts:
             L.check(lib.mpreid_rerank_finish_ex(nbr_all.data_ptr(), nbr_all.shape[1], v0_col.data_ptr(), v0_val.data_ptr(), v0_len.data_ptr(),
                                                 dist_qrows.data_ptr(), dist_qrows.stride(0), col0, _ptr(q_ids), row_max_q.data_ptr(), N, Q, Qs,
                                                 k1, k2, float(lambda_value), out.data_ptr(), out.stride(0), ws.data_ptr(), nbytes, part,
-                                                v0_col.shape[1], int(bool(rows_global)), _stream()), "rerank_finish")
-            if part == 1:
+                                                v0_col.shape[1], int(bool(rows_global)), int(qe_rows[0]), int(qe_rows[1]), _stream()),
+                    "rerank_finish")
+            if part & 25:
                 mark("rerank.expand_index")
             elif part & 2:
                 mark("rerank.jaccard_blend")
