@@ -770,7 +770,7 @@ def main():
     ap.add_argument("--k1", type=int, default=20)
     ap.add_argument("--k2", type=int, default=6)
     ap.add_argument("--cpu-queries", type=int, default=1500, help="queries in the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-rerank-n", type=int, default=6000, help="samples (Q+G) of the bounded CPU re-ranking baseline (0 = skip)")
+    ap.add_argument("--cpu-rerank-n", type=int, default=12000, help="samples (Q+G) of the bounded CPU re-ranking baseline (0 = skip)")
     ap.add_argument("--ref-queries", type=int, default=600, help="queries per step of the reference arm")
     ap.add_argument("--bf16-delta", action="store_true", help="also report mAP / rank-1 of the stated bf16 mode (default on for cctv)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")

@@ -216,9 +216,18 @@ def _rerank_sharded_fused(prep_all, nq, k1, k2, lambda_value, precision, group, 
     E.mark("rerank.all_pairs_gemm")
     keys, _ = E.cand_topk(cand, cnt, K, row_max, thr, partial=True)
     del cand
-    keys_all = torch.empty((world, N, K), dtype=torch.int64, device=dev)
-    all_gather_into(keys_all.view(-1), keys.view(-1), group)
-    nbr, nbr_val, status = E.merge_topk(keys_all, row_max, thr)
+    if _is_nccl(group) and os.environ.get("MPREID_SHARD_A2A", "1") != "0":
+        # every rank merges the rows of ITS shard: the partial keys of those rows arrive with one all-to-all (1/N of an
+        # all-gather), the merged lists (indices + values) are then all-gathered -- every rank needs all of them for V0
+        recv = torch.empty((world, hi - lo, K), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv.view(-1), keys.view(-1), [(hi - lo) * K] * world, [c * K for c in counts], group=group)
+        nbr_loc, val_loc, status = E.merge_topk(recv, row_max[lo:hi].contiguous(), thr[lo:hi].contiguous())
+        nbr = _allgather_contig(nbr_loc, counts, group)
+        nbr_val = _allgather_contig(val_loc, counts, group)
+    else:
+        keys_all = torch.empty((world, N, K), dtype=torch.int64, device=dev)
+        all_gather_into(keys_all.view(-1), keys.view(-1), group)
+        nbr, nbr_val, status = E.merge_topk(keys_all, row_max, thr)
     E.mark("rerank.topk")
     row_ids = torch.arange(lo, hi, device=dev, dtype=torch.int32)
     v0c, v0v, v0l = E.rerank_build_v0_sparse(row_ids, hi - lo, N, k1, nbr, nbr_val, row_max[lo:hi], prep_all.xn, prep_all.sqnorm)
