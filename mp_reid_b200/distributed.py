@@ -452,7 +452,11 @@ def _make_sharded_class():
             # the upload pieces that sub-block needs: the GEMMs of early sub-blocks run while later ones are still on
             # PCIe / NVLink, and the compute stream never waits for more than it is about to use.
             import os
-            sub = max(32, int(os.environ.get("MPREID_SHARD_SUB_ROWS", "8192")) // 32 * 32)
+            # (sub-block height: ~8,192 rows for two ranks, ~2,048 from four ranks on -- with many owners a stage is world
+            #  sub-blocks, and the GEMMs of the first stage should start soon after the queries have landed)
+            target = int(os.environ.get("MPREID_SHARD_SUB_ROWS", "8192" if world <= 2 else "2048"))
+            n_st = max(1, -(-S // max(32, target)))
+            sub = max(32, (-(-S // n_st) + 31) // 32 * 32)
             gfull = torch.empty((num_g, D), dtype=torch.float32, device=dev)
             xs = M._side_stream(dev, "exchange")
             main = torch.cuda.current_stream(dev)
@@ -524,7 +528,9 @@ def _make_sharded_class():
             qv = M._merge_adjacent([t for _, t in q_parts])
             q = E.prep_rows(qv[0] if len(qv) == 1 else torch.cat(qv, dim=0), normalize=norm, precision=self._precision, keep_xn=True)
             dmat = E.alloc_dist(nq, num_g, dev)
-            gf = torch.empty((num_g, D), dtype=torch.float32, device=dev)
+            simt = (self._precision or E.default_precision()).lower() in ("simt", "fp32_simt")
+            planes = None if simt else E.GalleryPlanes(num_g, D, dev, self._precision, keep_xn=True)
+            gf = torch.empty((num_g, D), dtype=torch.float32, device=dev) if simt else planes.xn
             # host-side software pipeline: the broadcasts of stage j+1 are enqueued before the GEMMs of stage j (an NCCL
             # call costs ~0.1 ms of host time; issuing all of them up front would delay the first GEMM by milliseconds)
             pending = exchange(0) if stages else []
@@ -532,8 +538,11 @@ def _make_sharded_class():
                 nxt = exchange(j + 1) if j + 1 < stages else []
                 for lo, hi, work in pending:
                     work.wait()                        # the compute stream waits for this sub-block only
-                    g = E.prep_rows(gfull[lo:hi], normalize=norm, precision=self._precision, xn_out=gf[lo:hi])
-                    E.dist_matrix(q, g, self._metric, self._precision, out=dmat[:, lo:hi])
+                    if planes is not None:             # two C calls on slices of buffers allocated once
+                        planes.add_block(gfull[lo:hi], lo, norm, q, self._metric, dmat)
+                    else:
+                        g = E.prep_rows(gfull[lo:hi], normalize=norm, precision=self._precision, xn_out=gf[lo:hi])
+                        E.dist_matrix(q, g, self._metric, self._precision, out=dmat[:, lo:hi])
                 pending = nxt
             # labels last: they were uploaded behind their features, the late ones land when the last piece does
             main.wait_stream(M._copy_stream(dev))

@@ -133,6 +133,73 @@ def prep_rows(x: torch.Tensor, normalize: bool, precision: str | None = None, ke
     return Prepared(n, D, Dp, xn, sqnorm, norm, hi, lo, bf, hh, hl, hscale)
 
 
+class GalleryPlanes:
+    """Operand planes, norms and normalised rows of a whole gallery, filled block by block as the rows arrive, each block
+    contracted against the prepared queries right away: prep_rows + dist_matrix on slices of buffers allocated ONCE.
+    A block costs two C calls and no allocation (~30 us of host time instead of ~150 us through prep_rows / dist_matrix),
+    which is what lets the sharded evaluator work in small sub-blocks (section 5 of DESIGN.md)."""
+
+    def __init__(self, num_g: int, D: int, device, precision: str | None = None, keep_xn: bool = True):
+        require_cuda()
+        self.lib = L.load()
+        self.precision = (precision or default_precision()).lower()
+        self.prec = L.PRECISIONS[self.precision]
+        if self.prec == L.FP32_SIMT:
+            raise ValueError("GalleryPlanes needs a tensor-core precision mode")
+        self.n, self.D, self.dev = num_g, D, device
+        pad = 64 if self.prec in (L.BF16, L.X3FP16, L.X2FP16) else 32
+        self.Dp = (D + pad - 1) // pad * pad
+        e = torch.empty
+        self.xn = e((num_g, D), dtype=torch.float32, device=device) if keep_xn else None
+        self.sqnorm = e((num_g,), dtype=torch.float32, device=device)
+        self.norm = e((num_g,), dtype=torch.float32, device=device)
+        self.hi = self.lo = self.bf = self.hh = self.hl = self.hscale = None
+        if self.prec in (L.X3FP16, L.X2FP16):
+            self.hh = e((num_g, self.Dp), dtype=torch.float16, device=device)
+            self.hl = e((num_g, self.Dp), dtype=torch.float16, device=device)
+            self.hscale = e((num_g,), dtype=torch.float32, device=device)
+            self.a, self.b, self.esz = self.hh, self.hl, 2
+        elif self.prec == L.X3TF32:
+            self.hi = e((num_g, self.Dp), dtype=torch.float32, device=device)
+            self.lo = e((num_g, self.Dp), dtype=torch.float32, device=device)
+            self.a, self.b, self.esz = self.hi, self.lo, 4
+        else:
+            self.bf = e((num_g, self.Dp), dtype=torch.bfloat16, device=device)
+            self.a, self.b, self.esz = self.bf, None, 2
+        self._p = {k: (None if t is None else t.data_ptr()) for k, t in dict(xn=self.xn, sq=self.sqnorm, nm=self.norm, hi=self.hi, lo=self.lo,
+                                                                             bf=self.bf, hh=self.hh, hl=self.hl, sc=self.hscale).items()}
+
+    def add_block(self, x: torch.Tensor, lo: int, normalize: bool, q: Prepared, metric: str, dmat: torch.Tensor):
+        """Rows x [n, D] (fp32, unit column stride, on the device) are gallery rows lo .. lo+n: prepare them in place and write
+        the distances of all queries to them into dmat[:, lo:lo+n]."""
+        n = x.shape[0]
+        with torch.cuda.device(self.dev):
+            self._add_block(x, n, lo, normalize, q, metric, dmat)
+
+    def _add_block(self, x, n, lo, normalize, q, metric, dmat):
+        p, Dp, D, st = self._p, self.Dp, self.D, _stream()
+        off = lambda base, per_row: None if base is None else base + lo * per_row
+        met = L.METRICS[metric]
+        L.check(self.lib.mpreid_prep_rows(x.data_ptr(), n, D, x.stride(0), int(bool(normalize)), off(p["xn"], 4 * D), D, off(p["sq"], 4), off(p["nm"], 4),
+                                          off(p["hi"], 4 * Dp), off(p["lo"], 4 * Dp), off(p["bf"], 2 * Dp), off(p["hh"], 2 * Dp), off(p["hl"], 2 * Dp),
+                                          off(p["sc"], 4), Dp, st), "prep_rows")
+        if met == L.ARCCOS:
+            qa, ga = q.norm.data_ptr(), off(p["nm"], 4)
+        elif met in (L.ONE_MINUS_DOT, L.DOT):
+            qa = ga = None
+        else:
+            qa, ga = q.sqnorm.data_ptr(), off(p["sq"], 4)
+        if self.prec == L.X3TF32:
+            qA, qB = q.hi, q.lo
+        elif self.prec in (L.X3FP16, L.X2FP16):
+            qA, qB = q.hh, q.hl
+        else:
+            qA, qB = q.bf, None
+        L.check(self.lib.mpreid_dist_matrix(qA.data_ptr(), _ptr(qB), self.a.data_ptr() + lo * Dp * self.esz,
+                                            None if self.b is None else self.b.data_ptr() + lo * Dp * self.esz, qa, ga, _ptr(q.hscale), off(p["sc"], 4),
+                                            q.n, n, Dp, Dp, met, self.prec, dmat.data_ptr() + 4 * lo, dmat.stride(0), None, st), "dist_matrix")
+
+
 def alloc_dist(Q: int, G: int, device) -> torch.Tensor:
     """[Q, G] fp32 view over a buffer whose leading dimension is padded to 128 B (vector stores, TMA)."""
     ld = (G + 31) // 32 * 32
