@@ -330,13 +330,14 @@ def run_ours(args, data, workload, wkey):
         t_loop = time.perf_counter()
         if os.environ.get("MPREID_BENCH_DEBUG"):
             torch.cuda.synchronize(); t_sync = time.perf_counter()
-        out = torch.empty((world, steps, slot_bytes), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(out.view(-1), dev_slots[:steps].reshape(-1))
+        # all slots travel, whatever `steps` is: the warm-up then runs the collectives at the timed run's sizes
+        out = torch.empty((world, n_slots, slot_bytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out.view(-1), dev_slots.view(-1))
         # every rank now holds every step's per-query results: the host reductions (numpy, global query order) are dealt out
         # over the ranks (step s on rank s % N) instead of queueing on rank 0's one host thread; the (cmc, mAP) of all
         # steps then meet on every rank with one tiny all-reduce
         mine = [s for s in range(steps) if s % world == rank]
-        res = torch.zeros((steps, 51), dtype=torch.float64, device=dev)
+        res = torch.zeros((n_slots, 51), dtype=torch.float64, device=dev)
         if mine:
             h = out[:, mine].cpu().numpy()
             counts = [MD.shard_bounds(Qall, world, r)[1] - MD.shard_bounds(Qall, world, r)[0] for r in range(world)] if strong else [Q] * world
