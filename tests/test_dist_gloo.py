@@ -41,6 +41,18 @@ def _worker(rank, world, port, golden, out_dir):
     r = orc.rank_eval(g["dist_euclid"][lo:hi], g["q_pid"][lo:hi], g_pid, g["q_cam"][lo:hi], g_cam) if hi > lo else None
     fh = torch.from_numpy(r["first_hit"]); ap = torch.from_numpy(r["ap"]); nr = torch.from_numpy(r["num_rel"])
     cmc, mAP = D.sharded_reduce(fh, ap, nr, counts, 50, g["dist_euclid"].shape[1])
+    # block-cyclic ownership (the fused row-sharded re-ranking): results travel with their global query index; with fewer
+    # than 256 queries rank 1 owns none and still takes part in the collective
+    full = orc.rank_eval(g["dist_euclid"], g["q_pid"], g_pid, g["q_cam"], g_cam)
+    for blk in (256, 16):     # 16: pretend blocks of 16 rows, so that both ranks own some
+        ids = torch.arange(Q)
+        ids = ids[(ids // blk) % world == rank]
+        if blk == 256:
+            assert torch.equal(ids, D.rerank_owned_queries(Q, world, rank))
+        sel = ids.numpy()
+        cmc2, mAP2 = D.sharded_reduce(torch.from_numpy(full["first_hit"][sel]), torch.from_numpy(full["ap"][sel]),
+                                      torch.from_numpy(full["num_rel"][sel]), None, 50, g["dist_euclid"].shape[1], ids=ids, total=Q)
+        assert np.array_equal(cmc2, cmc) and mAP2 == mAP
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), cmc=cmc, mAP=mAP)
     dist.barrier()
     dist.destroy_process_group()
