@@ -121,3 +121,115 @@ def test_aligned_shard_bounds_cover_and_align():
         b = [aligned_shard_bounds(n, w, r) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert all(lo % 32 == 0 or lo == n for lo, _ in b)
+
+
+# ------------------------------------------------------------------------------------------------
+# Collective sequence of the fused row-sharded re-ranking (distributed._rerank_sharded_fused): every rank must issue the
+# same exchanges in the same order, also a rank that owns no 256-row query block (fewer than world * 256 queries).
+# The CUDA calls are replaced by shape-only stand-ins, the collectives are the real ones (gloo).
+class _FakePrep:
+    def __init__(self, n, d):
+        self.n, self.sqnorm, self.xn = n, torch.ones(n), torch.zeros(n, d)
+
+    def take(self, ids):
+        return _FakePrep(int(ids.numel()), self.xn.shape[1])
+
+    def rows(self, lo, hi):
+        return _FakePrep(hi - lo, self.xn.shape[1])
+
+
+class _FakeEngine:
+    """Stand-in for mp_reid_b200.engine: tensors of the right shape and dtype, a log of the finish calls."""
+
+    def __init__(self, rank):
+        self.rank, self.finish_calls, self.K, self.C0, self.C1 = rank, [], 27, 40, 96
+
+    def rerank_neighbor_count(self, k1, k2):
+        return self.K
+
+    def mark(self, name):
+        pass
+
+    def dist_matrix(self, a, b, metric, precision):
+        return torch.zeros(a.n, b.n)
+
+    def row_kth(self, d, t, bound=False):
+        return torch.ones(d.shape[0])
+
+    def dist_symmetric_topk(self, x, thr, cap, nq, precision, own_mod=1, own_rank=0):
+        assert thr.shape == (x.n,) and (own_mod, own_rank) == (dist.get_world_size(), self.rank)
+        return (torch.zeros((x.n, cap), dtype=torch.int64), torch.zeros(x.n, dtype=torch.int32), torch.zeros(nq, x.n - nq), 0,
+                torch.full((x.n,), 1.0 + self.rank))
+
+    def cand_topk(self, cand, cnt, k, row_scale, thr, partial=False):
+        assert partial and bool((row_scale == float(dist.get_world_size())).all())    # maxima were max-reduced over the ranks
+        return torch.zeros((cand.shape[0], k), dtype=torch.int64), torch.zeros(4, dtype=torch.int32)
+
+    def merge_topk(self, keys_all, row_scale, thr):
+        P, n, k = keys_all.shape
+        return torch.zeros((n, k), dtype=torch.int32), torch.zeros((n, k)), torch.zeros(4, dtype=torch.int32)
+
+    def rerank_build_v0_sparse(self, row_ids, R, N, k1, nbr, nbr_val, row_max_rows, xn, sqnorm):
+        return (torch.zeros((R, self.C0), dtype=torch.int32), torch.zeros((R, self.C0), dtype=torch.float16),
+                torch.full((R,), 9 + self.rank, dtype=torch.int32))
+
+    def rerank_finish_workspace(self, N, Q, k1, k2, device):
+        self.v = (torch.zeros((N, self.C1), dtype=torch.int32), torch.zeros((N, self.C1), dtype=torch.float16), torch.zeros(N, dtype=torch.int32))
+        return torch.zeros(1, dtype=torch.uint8)
+
+    def rerank_finish_v_views(self, ws, N, Q, k1, k2):
+        return self.v
+
+    def alloc_dist(self, Q, G, device):
+        return torch.zeros(Q, G)
+
+    def rerank_finish(self, nbr, v0, block, q_ids, row_max, N, Q, k1, k2, lam, out=None, block_col0=None, rows_global=False, stages=7,
+                      ws=None, qe_rows=(0, 0)):
+        assert q_ids.numel() >= 1 and v0[0].shape[0] == N and v0[2].shape == (N,)      # the C entry rejects an empty query list
+        self.finish_calls.append((stages, int(q_ids.numel()), tuple(qe_rows)))
+        if stages == 8:
+            self.v[2][qe_rows[0]: qe_rows[1]] = 20 + self.rank                        # lengths of the rows this rank expanded
+            self.v[0][qe_rows[0]: qe_rows[1], :21] = self.rank + 1
+        return out if out is not None else torch.zeros(int(q_ids.numel()), N - Q)
+
+
+def _fused_worker(rank, world, port, nq, out_dir):
+    import datetime
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=60))
+    from mp_reid_b200 import distributed as D
+    N = 3001
+    log = {}
+    for k2 in (6, 1):
+        fake = _FakeEngine(rank)
+        D.E = fake
+        final, q_ids = D._rerank_sharded_fused(_FakePrep(N, 8), nq, 20, k2, 0.3, None, None, world, rank)
+        own = D.rerank_owned_queries(nq, world, rank)
+        assert torch.equal(q_ids, own) and tuple(final.shape) == (int(own.numel()), N - nq)
+        if k2 != 1:   # every rank holds every rank's expanded rows, trimmed to the longest one
+            lens = torch.cat([torch.full((D.shard_bounds(N, world, r)[1] - D.shard_bounds(N, world, r)[0],), 20 + r) for r in range(world)])
+            assert torch.equal(fake.v[2], lens.to(torch.int32))
+            assert bool((fake.v[0][:, :21] == (lens - 19).to(torch.int32)[:, None]).all()) and bool((fake.v[0][:, 21:] == 0).all())
+        log[k2] = fake.finish_calls
+    np.save(os.path.join(out_dir, f"calls{rank}.npy"), np.array([repr(log)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [200, 700])
+def test_fused_sharded_rerank_same_collectives_on_every_rank(tmp_path, nq):
+    """nq = 200: rank 1 owns no query block -- it must still expand its V rows and join every exchange (a rank that returned
+    early once left the others waiting in the all-reduce).  nq = 700: blocks 0, 2 on rank 0 and block 1 on rank 1."""
+    world = 2
+    mp.spawn(_fused_worker, args=(world, _free_port(), nq, str(tmp_path)), nprocs=world, join=True)
+    calls = [eval(str(np.load(tmp_path / f"calls{r}.npy")[0])) for r in range(world)]
+    own = [nq if nq <= 256 else 256 + (nq - 512), 0 if nq <= 256 else 256]
+    for r in range(world):
+        lo = r * 1501 if r else 0
+        hi = 1501 if r == 0 else 3001
+        if own[r]:
+            assert calls[r][6] == [(8, own[r], (lo, hi)), (16 | 4 | 2, own[r], (0, 0))]
+            assert calls[r][1] == [(7, own[r], (0, 0))]
+        else:     # idle rank: the expansion of its own rows only, with the placeholder query row
+            assert calls[r][6] == [(8, 1, (lo, hi))] and calls[r][1] == []
