@@ -309,6 +309,8 @@ def _rerank_sharded_plain(prep_all, nq, k1, k2, lambda_value, precision, group, 
     v0_all = tuple(gather(t) for t in v0)
     E.mark("rerank.v0")
     q_ids = ids32[:nq_local].contiguous()
+    if nq_local == 0:      # fewer queries than ranks: nothing to finish here (every exchange is behind us)
+        return torch.empty((0, N - nq), dtype=torch.float32, device=dev), torch.arange(q_lo, q_hi, device=dev)
     final_local = E.rerank_finish(nbr_all, v0_all, rows[:nq_local], q_ids, rm[:nq_local], N, nq, k1, k2, lambda_value)  # :73-99
     return final_local, torch.arange(q_lo, q_hi, device=dev)
 
