@@ -578,6 +578,32 @@ def run_ours(args, data, workload, wkey):
             "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
             "rerank": rerank, "mAP": float(mAP), "rank1": float(cmc[0]),
         }
+        if distributed:
+            try:
+                # SURVEY 8d "multi-GPU comm cost": bytes every rank RECEIVES per step (from the shapes; NVLink 5 = 900 GB/s per direction)
+                nvl = 900e9
+                g_own = MD.aligned_shard_bounds(G, world, 0)[1]
+                ex = float(G - g_own) * D * 4
+                lab_b = float(world) * 2 * g_own * 8
+                res_b = float(world) * 3 * max(Q, 1) * 8
+                comm = {"unit": "bytes received per rank per step", "nvlink_gbs_per_direction": 900,
+                        "value_arm": {"per_step": 0, "after_last_step": float(world) * n_slots * slot_bytes + n_slots * 51 * 8,
+                                      "note": "no collective inside the timed loop; one all-gather of the packed per-query results of all steps + one all-reduce of the (cmc, mAP) rows"},
+                        "e2e_arm": {"gallery_exchange": ex, "labels_allgather": lab_b, "per_query_results_allgather": res_b,
+                                    "nvlink_floor_ms": (ex + lab_b + res_b) / nvl * 1e3,
+                                    "exchange": os.environ.get("MPREID_SHARD_EXCHANGE", "p2p") + " (p2p: copy-engine pulls from symmetric memory; nccl: broadcasts)"}}
+                if rerank is not None:
+                    Nn, Kn = rerank["Q"] + rerank["G"], int(E.rerank_neighbor_count(args.k1, args.k2))
+                    keys_b = float(Nn) * Kn * 8                      # all-to-all: world pieces of (N / world) rows x K keys
+                    lists_b = float(Nn) * Kn * 8                     # merged neighbour lists: int32 index + fp32 value
+                    comm["rerank"] = {"thresholds_allgather": 4.0 * Nn, "row_max_allreduce": 4.0 * (Nn + 1), "partial_topk_keys_all_to_all": keys_b,
+                                      "neighbour_lists_allgather": lists_b,
+                                      "v0_rows_allgather": "N * W0 * 6 + 4 N, W0 = longest V0 row (<= (k1+1)(round(k1/2)+2) entries), decided at run time",
+                                      "expanded_rows_allgather": "N * W1 * 6 + 4 N, W1 = longest expanded row", "K": Kn,
+                                      "nvlink_floor_ms_fixed_part": (8.0 * Nn + 4 + keys_b + lists_b) / nvl * 1e3}
+                line["comm"] = comm
+            except Exception as e:      # reporting only: never lose the measured line over it
+                line["comm"] = {"error": f"{type(e).__name__}: {e}"}
         if args.bf16_delta and prec != "bf16":
             # stated low-precision mode (BASELINE config 2): one extra pass, outside every timed region
             pb = E.prep_rows(feats_dev, normalize=True, precision="bf16", keep_xn=False)
