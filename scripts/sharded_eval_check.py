@@ -6,7 +6,7 @@ bit for bit.  Prints 'SHARDED_EVAL_OK <world>' on rank 0.
     MPREID_CHECK_ONE_DEVICE=1        every rank uses cuda:0 (two ranks on a one-GPU box; needs gloo: NCCL refuses
                                      two ranks on one device)
 """
-import contextlib, io, os, sys
+import contextlib, datetime, io, os, sys
 import numpy as np, torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,10 +19,12 @@ if os.environ.get("MPREID_CHECK_ONE_DEVICE", "0") == "1":
     local = 0
 torch.cuda.set_device(local)
 os.environ["MPREID_DEVICE"] = f"cuda:{local}"
+# a rank that misses a collective must fail the check in minutes, not hold the GPUs for the default 10-30 minutes
+limit = datetime.timedelta(seconds=int(os.environ.get("MPREID_CHECK_TIMEOUT_S", "180")))
 if backend == "nccl":
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=limit)
 else:
-    dist.init_process_group(backend)
+    dist.init_process_group(backend, timeout=limit)
 rng = np.random.RandomState(21)
 Q, G, D = 1501, 9003, 320
 x = torch.from_numpy(rng.randn(Q + G, D).astype(np.float32))
