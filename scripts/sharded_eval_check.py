@@ -20,7 +20,7 @@ if os.environ.get("MPREID_CHECK_ONE_DEVICE", "0") == "1":
 torch.cuda.set_device(local)
 os.environ["MPREID_DEVICE"] = f"cuda:{local}"
 # a rank that misses a collective must fail the check in minutes, not hold the GPUs for the default 10-30 minutes
-limit = datetime.timedelta(seconds=int(os.environ.get("MPREID_CHECK_TIMEOUT_S", "180")))
+limit = datetime.timedelta(seconds=int(os.environ.get("MPREID_CHECK_TIMEOUT_S", "300")))
 if backend == "nccl":
     dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=limit)
 else:
