@@ -461,7 +461,6 @@ def _make_sharded_class():
             # broadcast each, issued asynchronously in the order (sub-block, owner) on a side stream that waits only for
             # the upload pieces that sub-block needs: the GEMMs of early sub-blocks run while later ones are still on
             # PCIe / NVLink, and the compute stream never waits for more than it is about to use.
-            import os
             # (sub-block height: ~8,192 rows for two ranks, ~2,048 from four ranks on -- with many owners a stage is world
             #  sub-blocks, and the GEMMs of the first stage should start soon after the queries have landed)
             target = int(os.environ.get("MPREID_SHARD_SUB_ROWS", "8192" if world <= 2 else "2048"))
